@@ -1,0 +1,114 @@
+"""Pin the CPU oracle (oracle/videomae_oracle.py) against fixtures produced by the real reference code
+(tools/make_golden.py: HF transformers VideoMAEForPreTraining + the reference's mask.py)."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import videomae_oracle as O
+
+
+def _load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name))
+
+
+def test_tube_and_random_masks_match_reference_generators(golden_dir):
+    g = _load(golden_dir, "masks.npz")
+    for name, size, ratio in (("tube_8x14x14_r90", (8, 14, 14), 0.9), ("tube_1x14x14_r90", (1, 14, 14), 0.9),
+                              ("tube_2x2x2_r50", (2, 2, 2), 0.5)):
+        np.random.seed(0)
+        got = np.stack([O.tube_mask(size, ratio) for _ in range(4)]).astype(np.uint8)
+        assert np.array_equal(got, g[name]), name
+    np.random.seed(0)
+    got = np.stack([O.random_mask((8, 14, 14), 0.9) for _ in range(2)]).astype(np.uint8)
+    assert np.array_equal(got, g["random_8x14x14_r90"])
+
+
+def test_tube_mask_structure():
+    np.random.seed(7)
+    m = O.tube_mask((8, 14, 14), 0.9).reshape(8, 196)
+    assert m.dtype == np.float64 and m.sum() == 8 * 176
+    assert (m == m[0]).all()  # one pattern repeated in every temporal slot
+
+
+def test_sinusoid_table_bit_equal(golden_dir):
+    g = _load(golden_dir, "sinusoid.npz")
+    for n, d in ((1568, 768), (1568, 384), (196, 192), (8, 64)):
+        t = O.sinusoid_table(n, d).numpy()
+        rows = g[f"n{n}_d{d}_rows"]
+        assert np.array_equal(t[rows], g[f"n{n}_d{d}"]), (n, d)
+
+
+def test_mask_to_index_is_boolean_indexing():
+    torch.manual_seed(0)
+    np.random.seed(1)
+    mask = O.batch_tube_masks(3, (2, 3, 3), 0.5)
+    x = torch.randn(3, 18, 5)
+    vis, msk = O.mask_to_index(mask)
+    assert torch.equal(x[~mask].reshape(3, -1, 5), torch.gather(x, 1, vis.long()[:, :, None].expand(-1, -1, 5)))
+    assert torch.equal(x[mask].reshape(3, -1, 5), torch.gather(x, 1, msk.long()[:, :, None].expand(-1, -1, 5)))
+    bad = mask.clone()
+    bad[0, :] = False
+    with pytest.raises(ValueError):
+        O.mask_to_index(bad)
+
+
+def test_patch_embed_order_is_conv3d():
+    cfg = O.make_config("tiny")
+    x = O.synthetic_clip(2, cfg, seed=3)
+    w = torch.randn(8, 3, 2, 16, 16)
+    ref = torch.nn.functional.conv3d(x.permute(0, 2, 1, 3, 4), w, stride=(2, 16, 16)).flatten(2).transpose(1, 2)
+    got = O.patchify_embed_order(x, cfg) @ w.reshape(8, -1).T
+    assert torch.allclose(ref, got, atol=2e-4, rtol=1e-4)
+
+
+def test_norm_pix_target_matches_hf_labels(golden_dir):
+    g = _load(golden_dir, "tiny_labels.npz")
+    cfg = O.make_config("tiny")
+    x = O.synthetic_clip(2, cfg, seed=5, image_like=True)
+    mask = torch.from_numpy(g["mask"])
+    _, msk = O.mask_to_index(mask)
+    got = O.norm_pix_target(x, msk, cfg).numpy()
+    assert np.array_equal(got, g["labels"])  # same fp32 ops in the same order -> bit-equal
+
+
+@pytest.mark.parametrize("tag,perturb", [("init", False), ("perturbed", True)])
+def test_tiny_step_loss_logits_grads(golden_dir, tag, perturb):
+    g = _load(golden_dir, "tiny_step.npz")
+    cfg = O.make_config("tiny")
+    params = O.init_params(cfg, seed=1, perturb=perturb)
+    x = O.synthetic_clip(3, cfg, seed=2, image_like=perturb)
+    mask = torch.from_numpy(g[f"{tag}.mask"])
+    np.random.seed(3)
+    assert torch.equal(mask, O.batch_tube_masks(3, cfg.grid, 0.5))
+    loss, logits, grads = O.grads_of(params, x, mask, cfg)
+    assert abs(float(loss) - float(g[f"{tag}.loss"])) <= 2e-6 * abs(float(g[f"{tag}.loss"]))
+    np.testing.assert_allclose(logits.numpy(), g[f"{tag}.logits"], rtol=1e-4, atol=2e-5)
+    for k, v in grads.items():
+        ref = g[f"{tag}.grad.{k}"]
+        denom = max(np.linalg.norm(ref), 1e-12)
+        assert np.linalg.norm(v.numpy() - ref) / denom < 2e-5, k
+
+
+def test_small_step_summary(golden_dir):
+    """BASELINE.json configs[0]: ViT-S/16, 16x224x224, tube mask 0.9, batch 2 (fp32 CPU)."""
+    with open(os.path.join(golden_dir, "small_step.json")) as f:
+        g = json.load(f)
+    cfg = O.make_config("small")
+    params = O.init_params(cfg, seed=0, perturb=True)
+    x = O.synthetic_clip(2, cfg, seed=0, image_like=True)
+    np.random.seed(0)
+    mask = O.batch_tube_masks(2, cfg.grid, 0.9)
+    loss, logits, grads = O.grads_of(params, x, mask, cfg)
+    ref = g["perturbed"]
+    assert abs(float(loss) - ref["loss"]) <= 1e-5 * ref["loss"]
+    samp = logits.flatten()[::ref["logits_sample_stride"]][:64].numpy()
+    np.testing.assert_allclose(samp, np.array(ref["logits_sample"]), rtol=2e-3, atol=2e-4)
+    for k, v in grads.items():
+        assert abs(float(v.double().norm()) - ref["grad_norms"][k]) <= 1e-4 * ref["grad_norms"][k] + 1e-9, k
+
+
+def test_loss_allreduce_is_mean():
+    assert abs(O.loss_allreduce([1.0, 3.0]) - 2.0) < 1e-12

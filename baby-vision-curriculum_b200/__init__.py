@@ -1,0 +1,7 @@
+"""bvc-b200: the VideoMAE pretraining step of ssheybani/baby-vision-curriculum on hand-written sm_100a kernels.
+
+The directory name carries a hyphen (it mirrors the reference repository's name), so import it through the
+`bvc_b200` shim at the repository root:  `import bvc_b200 as bvc`.
+"""
+from . import _lib  # noqa: F401
+from ._lib import BvcError, load as load_library  # noqa: F401

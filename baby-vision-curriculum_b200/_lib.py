@@ -1,0 +1,246 @@
+"""ctypes binding of libbvc.so (include/bvc.h).  No fallback: if the library is missing or a call fails, raise.
+
+Every wrapper takes torch CUDA tensors, passes raw device pointers plus the current CUDA stream, and returns nothing;
+outputs are pre-allocated by the caller (torch is the allocator / stream owner, not the compute path).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libbvc.so")
+ABI_VERSION = 3
+
+_lib = None
+
+
+class BvcError(RuntimeError):
+    pass
+
+
+class GemmArgs(C.Structure):
+    _fields_ = [
+        ("a", C.c_void_p), ("b", C.c_void_p), ("lda", C.c_int64), ("ldb", C.c_int64),
+        ("a_mn_major", C.c_int32), ("b_mn_major", C.c_int32),
+        ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32), ("k_splits", C.c_int32),
+        ("out_f32", C.c_void_p), ("out_bf16", C.c_void_p), ("ldo", C.c_int64),
+        ("out_seg", C.c_int32), ("out_seg_stride", C.c_int32), ("out_seg_off", C.c_int32),
+        ("alpha_host", C.c_float), ("alpha_dev", C.c_void_p), ("bias", C.c_void_p),
+        ("act", C.c_int32), ("aux_out", C.c_void_p), ("aux_in", C.c_void_p), ("ld_aux", C.c_int64),
+        ("res", C.c_void_p), ("ldr", C.c_int64), ("res_idx", C.c_void_p),
+        ("target", C.c_void_p), ("ldt", C.c_int64), ("loss_partial", C.c_void_p), ("logits_out", C.c_void_p),
+        ("block_n", C.c_int32),
+    ]
+
+
+_SIGNATURES = {
+    "bvc_abi_version": (C.c_int, []),
+    "bvc_mask_count": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "bvc_mask_to_index": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.c_void_p, C.c_void_p]),
+    "bvc_patchify_target": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int32] * 8 + [C.c_void_p, C.c_void_p, C.c_int32,
+                                                                                  C.c_void_p]),
+    "bvc_gemm_bf16": (C.c_int, [C.POINTER(GemmArgs), C.c_void_p]),
+    "bvc_gemm_loss_slots": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32]),
+    "bvc_loss_finalize": (C.c_int, [C.c_void_p, C.c_int64, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "bvc_layernorm_fwd": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+                                    C.c_float, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "bvc_layernorm_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
+                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+                                    C.c_void_p, C.c_void_p, C.c_void_p]),
+    "bvc_colsum": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                             C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "bvc_cast_f32_to_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "bvc_rows_to_bf16": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                   C.c_void_p, C.c_void_p]),
+    "bvc_decoder_mask_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
+                                        C.c_int32, C.c_int32, C.c_void_p]),
+    "bvc_attn_fwd": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_void_p, C.c_void_p,
+                               C.c_void_p]),
+    "bvc_attn_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                               C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
+}
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+
+def load():
+    """Load libbvc.so once; raise BvcError (never fall back) when it is missing or has the wrong ABI."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise BvcError(f"{LIB_PATH} not found: build it with `python baby-vision-curriculum_b200/build.py` "
+                       "(there is no CPU or PyTorch fallback for the CUDA path)")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError here == missing export
+        fn.restype = res
+        fn.argtypes = args
+    v = lib.bvc_abi_version()
+    if v != ABI_VERSION:
+        raise BvcError(f"libbvc.so ABI {v} != expected {ABI_VERSION}; rebuild")
+    _lib = lib
+    return lib
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    if t is None:
+        return None
+    return C.c_void_p(t.data_ptr())
+
+
+def _check(rc, what):
+    if rc != 0:
+        raise BvcError(f"{what} failed with code {rc} (see stderr)")
+
+
+_launches = 0
+
+
+def launch_count():
+    """Number of libbvc.so kernel-launching calls made so far in this process (bench.py's gpu_launches)."""
+    return _launches
+
+
+def _count(n=1):
+    global _launches
+    _launches += n
+
+
+def _cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise BvcError("libbvc.so kernels need CUDA tensors; there is no CPU path")
+
+
+# ------------------------------------------------------------------------------------------------ wrappers
+def mask_count(mask_u8, n_visible):
+    _cuda(mask_u8, n_visible)
+    B, N = mask_u8.shape
+    _check(load().bvc_mask_count(_p(mask_u8), B, N, _p(n_visible), _stream()), "bvc_mask_count")
+    _count()
+
+
+def mask_to_index(mask_u8, nv, vis_idx, msk_idx, slot, status):
+    _cuda(mask_u8, vis_idx, msk_idx, slot, status)
+    B, N = mask_u8.shape
+    _check(load().bvc_mask_to_index(_p(mask_u8), B, N, nv, _p(vis_idx), _p(msk_idx), _p(slot), _p(status), _stream()),
+           "bvc_mask_to_index")
+    _count()
+
+
+def patchify_target(pixels, slot, ts, ps, nv, patches_vis, target, norm_pix=True):
+    _cuda(pixels, slot, patches_vis, target)
+    B, T, Cc, H, W = pixels.shape
+    _check(load().bvc_patchify_target(_p(pixels), _p(slot), B, T, Cc, H, W, ts, ps, nv, _p(patches_vis), _p(target),
+                                      1 if norm_pix else 0, _stream()), "bvc_patchify_target")
+    _count()
+
+
+def gemm(a, b, M, N, K, *, lda=None, ldb=None, a_mn=False, b_mn=False, out_f32=None, out_bf16=None, ldo=None,
+         out_seg=0, out_seg_stride=0, out_seg_off=0, alpha=1.0, alpha_dev=None, bias=None, act=0, aux_out=None,
+         aux_in=None, ld_aux=0, res=None, ldr=0, res_idx=None, target=None, ldt=0, loss_partial=None,
+         logits_out=None, k_splits=1, block_n=0):
+    """out = epilogue(alpha * A . B^T); see include/bvc.h bvc_gemm_bf16 for the epilogue order."""
+    _cuda(a, b, out_f32, out_bf16)
+    g = GemmArgs()
+    g.a, g.b = a.data_ptr(), b.data_ptr()
+    g.lda = lda if lda is not None else (M if a_mn else K)
+    g.ldb = ldb if ldb is not None else (N if b_mn else K)
+    g.a_mn_major, g.b_mn_major = int(a_mn), int(b_mn)
+    g.M, g.N, g.K, g.k_splits = M, N, K, k_splits
+    g.out_f32 = out_f32.data_ptr() if out_f32 is not None else None
+    g.out_bf16 = out_bf16.data_ptr() if out_bf16 is not None else None
+    g.ldo = ldo if ldo is not None else N
+    g.out_seg, g.out_seg_stride, g.out_seg_off = out_seg, out_seg_stride, out_seg_off
+    g.alpha_host = alpha
+    g.alpha_dev = alpha_dev.data_ptr() if alpha_dev is not None else None
+    g.bias = bias.data_ptr() if bias is not None else None
+    g.act = act
+    g.aux_out = aux_out.data_ptr() if aux_out is not None else None
+    g.aux_in = aux_in.data_ptr() if aux_in is not None else None
+    g.ld_aux = ld_aux
+    g.res = res.data_ptr() if res is not None else None
+    g.ldr = ldr
+    g.res_idx = res_idx.data_ptr() if res_idx is not None else None
+    g.target = target.data_ptr() if target is not None else None
+    g.ldt = ldt
+    g.loss_partial = loss_partial.data_ptr() if loss_partial is not None else None
+    g.logits_out = logits_out.data_ptr() if logits_out is not None else None
+    g.block_n = block_n
+    _check(load().bvc_gemm_bf16(C.byref(g), _stream()), "bvc_gemm_bf16")
+    _count()
+
+
+def gemm_loss_slots(M, N, block_n=0):
+    return int(load().bvc_gemm_loss_slots(M, N, block_n))
+
+
+def loss_finalize(partials, numel, status, loss):
+    _cuda(partials, loss)
+    _check(load().bvc_loss_finalize(_p(partials), partials.numel(), float(numel), _p(status), _p(loss), _stream()),
+           "bvc_loss_finalize")
+    _count()
+
+
+def layernorm_fwd(x, gamma, beta, eps, M, d, y, mean, rstd, ldx=None, seg=(0, 0, 0)):
+    _cuda(x, gamma, beta, y, mean, rstd)
+    _check(load().bvc_layernorm_fwd(_p(x), ldx if ldx is not None else d, seg[0], seg[1], seg[2], _p(gamma), _p(beta),
+                                    eps, M, d, _p(y), _p(mean), _p(rstd), _stream()), "bvc_layernorm_fwd")
+    _count()
+
+
+def layernorm_bwd(dy, x, mean, rstd, gamma, dres, M, d, dx_f32, dx_bf16, dgamma, dbeta, ldx=None, seg=(0, 0, 0)):
+    _cuda(dy, x, mean, rstd, gamma, dgamma, dbeta)
+    _check(load().bvc_layernorm_bwd(_p(dy), _p(x), ldx if ldx is not None else d, seg[0], seg[1], seg[2], _p(mean),
+                                    _p(rstd), _p(gamma), _p(dres), M, d, _p(dx_f32), _p(dx_bf16), _p(dgamma),
+                                    _p(dbeta), _stream()), "bvc_layernorm_bwd")
+    _count()
+
+
+def colsum(inp, M, N, out, ld=None, seg=(0, 0, 0), scale=1.0, scale_dev=None):
+    _cuda(inp, out)
+    is_f32 = 1 if inp.dtype == torch.float32 else 0
+    _check(load().bvc_colsum(_p(inp), is_f32, ld if ld is not None else N, seg[0], seg[1], seg[2], M, N, scale,
+                             _p(scale_dev), _p(out), _stream()), "bvc_colsum")
+    _count()
+
+
+def cast_bf16(src, dst):
+    _cuda(src, dst)
+    _check(load().bvc_cast_f32_to_bf16(_p(src), _p(dst), src.numel(), _stream()), "bvc_cast_f32_to_bf16")
+    _count()
+
+
+def rows_to_bf16(src, M, d, dst, ld=None, seg=(0, 0, 0)):
+    _cuda(src, dst)
+    _check(load().bvc_rows_to_bf16(_p(src), ld if ld is not None else d, seg[0], seg[1], seg[2], M, d, _p(dst),
+                                   _stream()), "bvc_rows_to_bf16")
+    _count()
+
+
+def decoder_mask_rows(x, mask_token, pos, msk_idx, B, N, nv, d):
+    _cuda(x, mask_token, pos, msk_idx)
+    _check(load().bvc_decoder_mask_rows(_p(x), _p(mask_token), _p(pos), _p(msk_idx), B, N, nv, d, _stream()),
+           "bvc_decoder_mask_rows")
+    _count()
+
+
+def attn_fwd(qkv, B, S, H, scale, out, lse):
+    _cuda(qkv, out, lse)
+    _check(load().bvc_attn_fwd(_p(qkv), B, S, H, scale, _p(out), _p(lse), _stream()), "bvc_attn_fwd")
+    _count()
+
+
+def attn_bwd(qkv, out, dout, lse, B, S, H, scale, delta, dqkv):
+    _cuda(qkv, out, dout, lse, delta, dqkv)
+    _check(load().bvc_attn_bwd(_p(qkv), _p(out), _p(dout), _p(lse), B, S, H, scale, _p(delta), _p(dqkv), _stream()),
+           "bvc_attn_bwd")
+    _count(2)

@@ -63,12 +63,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug turns into a trap (-> cudaErrorLaunchFailure at the C-ABI) instead of
-// a hung GPU.  try_wait itself sleeps in hardware, so the spin count is small in healthy runs.
+// Bounded wait: a protocol bug turns into a trap (-> cudaErrorLaunchFailure at the C-ABI) after ~2 s of wall
+// time instead of a hung GPU.  try_wait itself sleeps in hardware, so healthy runs rarely reach the timer read.
+__device__ __forceinline__ uint64_t global_timer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t spins = 0;
+  if (mbar_try_wait(bar, parity)) return;
+  const uint64_t t0 = global_timer_ns();
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 26)) {
+    if (global_timer_ns() - t0 > 2000000000ull) {
       printf("bvc: mbarrier watchdog fired (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
       __trap();
     }

@@ -11,7 +11,10 @@
  *   - returns 0 on success, <0 on error (BVC_ERR_*); never throws, never allocates, never synchronises;
  *   - `stream` is a cudaStream_t passed as void*; re-entrant across streams and host threads (backward runs on
  *     the autograd engine's thread);
- *   - bf16 = __nv_bfloat16 storage (uint16), row-major, leading dimensions in ELEMENTS.
+ *   - bf16 = __nv_bfloat16 storage (uint16), row-major, leading dimensions in ELEMENTS;
+ *   - "segment remap" (seg, seg_stride, seg_off): logical row r of a compact [rows, d] operand lives at physical
+ *     row (r / seg) * seg_stride + (r % seg) + seg_off of a [B * seg_stride, d] buffer; seg == 0 means identity.
+ *     It expresses "the Nv visible rows" / "the last Nm rows" of every clip of a [B, N, d] tensor (HF:506, HF:591).
  */
 #ifndef BVC_H_
 #define BVC_H_
@@ -25,27 +28,58 @@ extern "C" {
 #define BVC_ERR_ARG (-1)
 #define BVC_ERR_DRIVER (-2)
 #define BVC_ERR_LAUNCH (-3)
+#define BVC_ABI_VERSION 3
 
-/* library / build info: returns the ABI version (bumped when a signature changes) */
+/* library / build info: returns BVC_ABI_VERSION (bumped when a signature changes) */
 int bvc_abi_version(void);
+
+/* ------------------------------------------------------------------------------------------------------
+ * Tube-mask indexing.  Replaces the boolean-index ops `x[~bool_masked_pos]` / `x[bool_masked_pos]`
+ * (HF:121-122, HF:587-588, HF:669-670; mask built at pretrain_videomae.py:294-298).  Bit-exact integer work.
+ *   mask        uint8/bool [B, N], non-zero = masked
+ *   bvc_mask_count:    n_visible[b] = #zeros of row b
+ *   bvc_mask_to_index: vis_idx [B, nv] / msk_idx [B, N-nv] = ascending token ids of the visible / masked tokens;
+ *                      slot [B, N] = position of token n in the decoder sequence [visible asc ; masked asc]
+ *                      (slot < nv <=> visible); status[0] |= 1 if some row does not have exactly nv visible
+ *                      tokens (HF's reshape raises in that case; the caller turns the flag into an error / NaN loss)
+ * ------------------------------------------------------------------------------------------------------ */
+int bvc_mask_count(const uint8_t* mask, int32_t B, int32_t N, int32_t* n_visible, void* stream);
+int bvc_mask_to_index(const uint8_t* mask, int32_t B, int32_t N, int32_t nv, int32_t* vis_idx, int32_t* msk_idx,
+                      int32_t* slot, int32_t* status, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * Tubelet patchify + normalised-pixel target in one HBM pass (TMA-staged rows of patches).
+ * Replaces the Conv3d im2col/cast of HF:175-176 (visible tokens only: gather-first, HF:119-122) and the whole
+ * label construction HF:598-670.
+ *   pixels      fp32 [B, T, C=3, H, W] contiguous; patch 16x16, tubelet ts in {1, 2}; W <= 256
+ *   slot        from bvc_mask_to_index
+ *   patches_vis bf16 [B*nv, K]      K = 3*ts*256, k = ((c*ts + t)*16 + ph)*16 + pw   (Conv3d weight order)
+ *   target      fp32 [B*(N-nv), K]  f = ((t*16 + ph)*16 + pw)*3 + c; if norm_pix:
+ *               (p - mean) / (sqrt(var_unbiased) + 1e-6) per (token, channel) with p = x*std_IN[c] + mean_IN[c],
+ *               else p itself (HF:644-667)
+ * ------------------------------------------------------------------------------------------------------ */
+int bvc_patchify_target(const float* pixels, const int32_t* slot, int32_t B, int32_t T, int32_t C, int32_t H,
+                        int32_t W, int32_t ts, int32_t ps, int32_t nv, void* patches_vis, float* target,
+                        int32_t norm_pix, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------
  * Dense contraction on the tcgen05 tensor cores:   out[M,N] = epilogue( alpha * A[M,K] . B[N,K]^T )
  * Replaces every F.linear / Conv3d-as-GEMM on the path: HF:175-176 (tubelet embedding), HF:239-242 (q,k,v),
  * HF:281-284 (attention out-proj), HF:314-317 (fc1+GELU), HF:327-331 (fc2+residual), HF:576 (encoder_to_decoder),
- * HF:510 (decoder head) and their autograd backward (dgrad / wgrad).
+ * HF:510 (decoder head) + HF:672-673 (MSE) and their autograd backward (dgrad / wgrad).
  *
  * Operand storage: a_mn_major == 0: A is stored [M, K] row-major (K contiguous), lda >= K.
  *                  a_mn_major == 1: A is stored [K, M] row-major (M contiguous), lda >= M  (i.e. A^T in memory).
  *                  same for B with N.   Forward = (0,0); dgrad dX = dY.W = (0,1); wgrad dW = dY^T.X = (1,1).
+ * Requirements: lda, ldb, ldo, ld_aux multiples of 8; N multiple of 8; pointers 16-byte aligned.
  * Epilogue, in this order, per output element (r, c):
  *     v = alpha_host * (alpha_dev ? *alpha_dev : 1) * acc + (bias ? bias[c] : 0)
- *     act == 1 (GELU, exact erf, HF:316):  if aux_out: aux_out[r*ld_aux+c] = bf16(v);  v = gelu(v)
+ *     act == 1 (GELU, exact erf, HF:316):  v = bf16(v); if aux_out: aux_out[r*ld_aux+c] = v;  v = gelu(v)
  *     act == 2 (GELU backward):            v *= gelu'(aux_in[r*ld_aux+c])
  *     if res:     v += res[(res_idx ? res_idx[r] : r) * ldr + c]          (fp32 residual / position table)
- *     if target:  (masked-MSE, HF:672-673)  if logits_out: logits_out[r*ldo+c] = bf16(v);
- *                 v -= target[r*ldt+c];  *loss_acc += v*v  (double, atomically, one add per warp)
- *     row remap:  R = out_seg > 0 ? (r / out_seg) * out_seg_stride + (r % out_seg) + out_seg_off : r
+ *     if target:  (masked MSE, HF:672-673)  if logits_out: logits_out[r*ldo+c] = bf16(v);
+ *                 v -= target[r*ldt+c];  tile partial of sum(v*v) -> loss_partial (see bvc_gemm_loss_slots)
+ *     R = segment remap of r with (out_seg, out_seg_stride, out_seg_off)
  *     store:      k_splits > 1 -> atomicAdd(out_f32[R*ldo+c], v)   (caller zero-fills out_f32; no bias/act/res)
  *                 else out_f32[R*ldo+c] = v and/or out_bf16[R*ldo+c] = bf16(v)
  * ------------------------------------------------------------------------------------------------------ */
@@ -55,7 +89,7 @@ typedef struct bvc_gemm_args {
   int64_t lda, ldb;
   int32_t a_mn_major, b_mn_major;
   int32_t M, N, K;
-  int32_t k_splits;       /* >= 1; > 1 only with out_f32 (atomic accumulate) */
+  int32_t k_splits;       /* >= 1; > 1 only with out_f32 (atomic accumulate); 0 = choose (wgrad shapes) */
   float* out_f32;
   void* out_bf16;
   int64_t ldo;
@@ -72,12 +106,67 @@ typedef struct bvc_gemm_args {
   const int32_t* res_idx;
   const float* target;
   int64_t ldt;
-  double* loss_acc;
+  float* loss_partial;    /* fp32 [bvc_gemm_loss_slots(M, N, block_n)], every slot written by the call */
   void* logits_out;       /* bf16, ld = ldo */
   int32_t block_n;        /* 0 = choose; else 64 / 128 / 192 / 256 */
 } bvc_gemm_args;
 
 int bvc_gemm_bf16(const bvc_gemm_args* args, void* stream);
+/* number of fp32 partial sums a target/loss GEMM of this shape writes (block_n as passed to the call) */
+int64_t bvc_gemm_loss_slots(int32_t M, int32_t N, int32_t block_n);
+/* loss = sum(partials) / numel (fixed order, double accumulation: deterministic); NaN when status[0] != 0 */
+int bvc_loss_finalize(const float* partials, int64_t n, double numel, const int32_t* status, float* loss,
+                      void* stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * LayerNorm (HF:352, HF:360 eps 1e-12; decoder.norm HF:508 eps 1e-5), fp32 statistics, one warp per row.
+ *   x fp32 [*, d] with segment remap (x_seg...) ; y bf16 [M, d] compact; mean/rstd fp32 [M].  d % 4 == 0, d <= 1024.
+ * Backward: dx = rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * gamma  (+ dres if given);
+ *   dx_f32 / dx_bf16 (either may be null) are written at the remapped rows, dres read at the remapped rows;
+ *   dgamma/dbeta fp32 [d] are ACCUMULATED atomically (caller zero-fills).
+ * ------------------------------------------------------------------------------------------------------ */
+int bvc_layernorm_fwd(const float* x, int64_t ldx, int32_t x_seg, int32_t x_seg_stride, int32_t x_seg_off,
+                      const float* gamma, const float* beta, float eps, int32_t M, int32_t d, void* y,
+                      float* mean, float* rstd, void* stream);
+int bvc_layernorm_bwd(const void* dy, const float* x, int64_t ldx, int32_t x_seg, int32_t x_seg_stride,
+                      int32_t x_seg_off, const float* mean, const float* rstd, const float* gamma,
+                      const float* dres, int32_t M, int32_t d, float* dx_f32, void* dx_bf16, float* dgamma,
+                      float* dbeta, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * Column sums (bias gradients; mask_token gradient HF:528/591): out[c] += scale * sum_r in[row(r), c].
+ *   in_is_f32 selects fp32 / bf16 input; segment remap on the input rows; out fp32 [N] accumulated atomically
+ *   (caller zero-fills); scale = scale_host * (scale_dev ? *scale_dev : 1).  N % 8 == 0.
+ * ------------------------------------------------------------------------------------------------------ */
+int bvc_colsum(const void* in, int32_t in_is_f32, int64_t ld, int32_t seg, int32_t seg_stride, int32_t seg_off,
+               int32_t M, int32_t N, float scale_host, const float* scale_dev, float* out, void* stream);
+
+/* fp32 -> bf16 cast of n contiguous elements (per-step weight cast that autocast does per call, HF linear layers) */
+int bvc_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream);
+/* rows of an fp32 [*, d] buffer (segment remap) -> compact bf16 [M, d]  (d % 4 == 0) */
+int bvc_rows_to_bf16(const float* src, int64_t ld, int32_t seg, int32_t seg_stride, int32_t seg_off, int32_t M,
+                     int32_t d, void* dst, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * Decoder input, mask-token half (HF:588-591): x[b, nv + j, :] = mask_token + pos[msk_idx[b, j], :]
+ *   x fp32 [B, N, d]; pos fp32 [N, d]; msk_idx int32 [B, N-nv].  (The visible half is written by the
+ *   encoder_to_decoder GEMM epilogue: res = pos, res_idx = vis_idx, out_seg = nv, out_seg_stride = N.)
+ * ------------------------------------------------------------------------------------------------------ */
+int bvc_decoder_mask_rows(float* x, const float* mask_token, const float* pos, const int32_t* msk_idx, int32_t B,
+                          int32_t N, int32_t nv, int32_t d, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * Multi-head self-attention, head_dim 64, no mask, no dropout (HF:236-266 + sdpa / HF:181-206), flash-style on
+ * tcgen05: S = Q K^T and O = P V accumulate in TMEM, softmax in fp32 registers.
+ *   qkv  bf16 [B, S, 3, H, 64]  (= the fused QKV GEMM output [B*S, 3*H*64])
+ *   out  bf16 [B, S, H*64];  lse fp32 [B, H, S] (natural-log sum-exp of the scaled scores)
+ * Backward: dqkv bf16 [B, S, 3, H, 64] from dout bf16 [B, S, H*64], recomputing P from lse.
+ *   delta fp32 [B, H, S] is scratch (rowsum(dO * O)).
+ * ------------------------------------------------------------------------------------------------------ */
+int bvc_attn_fwd(const void* qkv, int32_t B, int32_t S, int32_t H, float scale, void* out, float* lse,
+                 void* stream);
+int bvc_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, int32_t B, int32_t S,
+                 int32_t H, float scale, float* delta, void* dqkv, void* stream);
 
 #ifdef __cplusplus
 }

@@ -5,3 +5,11 @@ The directory name carries a hyphen (it mirrors the reference repository's name)
 """
 from . import _lib  # noqa: F401
 from ._lib import BvcError, load as load_library  # noqa: F401
+from .modeling_videomae import (  # noqa: F401
+    VideoMAEConfig,
+    VideoMAEForPreTraining,
+    VideoMAEForPreTrainingOutput,
+    get_sinusoid_encoding_table,
+)
+from .masking import TubeMaskingGenerator, RandomMaskingGenerator, batch_masks  # noqa: F401
+from .ddputils import AllReduce  # noqa: F401

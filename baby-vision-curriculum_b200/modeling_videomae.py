@@ -1,0 +1,300 @@
+"""Drop-in replacement for transformers.VideoMAEForPreTraining on the reference's hot path.
+
+Boundary (pretraining/generative/pretrain_videomae.py:301):
+    outputs = xmodel(inputs, bool_masked_pos=bool_masked_pos);  loss = outputs.loss
+Contract kept: constructed from a VideoMAEConfig-like object, `.config` readable,
+HF-identical parameter names / shapes / init (state-dicts load both ways, strict), real nn.Parameters so the model
+wraps in torch DDP, every parameter receives a gradient each step, loss is an fp32 0-dim tensor with autograd
+history that honours an arbitrary upstream grad (GradScaler), ValueError on channel / size mismatch or missing mask.
+The module tree below only *holds* parameters under HF's names; all arithmetic is libbvc.so (engine.py).
+"""
+from __future__ import annotations
+
+import os
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+import torch
+from torch import nn
+
+from . import _lib as L
+from .engine import BF16, F32, Bf16Cache, BlockFn, EmbedFn, EncToDecFn, HeadLossFn, StepState
+
+
+@dataclass
+class VideoMAEConfig:
+    """The fields of transformers.VideoMAEConfig this path reads, with HF's defaults
+    (transformers/models/videomae/configuration_videomae.py:60-80).  A real transformers.VideoMAEConfig works too."""
+
+    image_size: int = 224
+    patch_size: int = 16
+    num_channels: int = 3
+    num_frames: int = 16
+    tubelet_size: int = 2
+    hidden_size: int = 768
+    num_hidden_layers: int = 12
+    num_attention_heads: int = 12
+    intermediate_size: int = 3072
+    hidden_act: str = "gelu"
+    hidden_dropout_prob: float = 0.0
+    attention_probs_dropout_prob: float = 0.0
+    initializer_range: float = 0.02
+    layer_norm_eps: float = 1e-12
+    qkv_bias: bool = True
+    use_mean_pooling: bool = True
+    decoder_num_attention_heads: int = 6
+    decoder_hidden_size: int = 384
+    decoder_num_hidden_layers: int = 4
+    decoder_intermediate_size: int = 1536
+    norm_pix_loss: bool = True
+
+
+@dataclass
+class VideoMAEForPreTrainingOutput:
+    """HF:64-75."""
+
+    loss: Optional[torch.Tensor] = None
+    logits: Optional[torch.Tensor] = None
+    hidden_states: Optional[tuple] = None
+    attentions: Optional[tuple] = None
+
+    def __getitem__(self, i):
+        return tuple(v for v in (self.loss, self.logits, self.hidden_states, self.attentions) if v is not None)[i]
+
+
+def get_sinusoid_encoding_table(n_position: int, d_hid: int) -> torch.Tensor:
+    """HF:78-91 in closed form (float64 through numpy, stored fp32) -- bit-equal to HF's table. [n_position, d_hid]."""
+    pos = np.arange(n_position, dtype=np.float64)[:, None]
+    j = np.arange(d_hid)
+    ang = pos / np.power(10000, 2 * (j // 2) / d_hid)[None, :]
+    ang[:, 0::2] = np.sin(ang[:, 0::2])
+    ang[:, 1::2] = np.cos(ang[:, 1::2])
+    return torch.from_numpy(ang).to(torch.float32)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# parameter containers under HF's module / parameter names (never called)
+# ---------------------------------------------------------------------------------------------------------------
+class _Holder(nn.Module):
+    def forward(self, *a, **k):  # pragma: no cover
+        raise RuntimeError("parameter container: the arithmetic runs in libbvc.so through VideoMAEForPreTraining")
+
+
+class VideoMAEPatchEmbeddings(_Holder):
+    def __init__(self, c):
+        super().__init__()
+        self.projection = nn.Conv3d(c.num_channels, c.hidden_size, kernel_size=(c.tubelet_size, c.patch_size, c.patch_size),
+                                    stride=(c.tubelet_size, c.patch_size, c.patch_size))
+
+
+class VideoMAEEmbeddings(_Holder):
+    def __init__(self, c):
+        super().__init__()
+        self.patch_embeddings = VideoMAEPatchEmbeddings(c)
+
+
+class VideoMAESelfAttention(_Holder):
+    def __init__(self, d):
+        super().__init__()
+        self.query = nn.Linear(d, d, bias=False)
+        self.key = nn.Linear(d, d, bias=False)
+        self.value = nn.Linear(d, d, bias=False)
+        self.q_bias = nn.Parameter(torch.zeros(d))
+        self.v_bias = nn.Parameter(torch.zeros(d))
+
+
+class VideoMAESelfOutput(_Holder):
+    def __init__(self, d):
+        super().__init__()
+        self.dense = nn.Linear(d, d)
+
+
+class VideoMAEAttention(_Holder):
+    def __init__(self, d):
+        super().__init__()
+        self.attention = VideoMAESelfAttention(d)
+        self.output = VideoMAESelfOutput(d)
+
+
+class _Dense(_Holder):
+    def __init__(self, i, o):
+        super().__init__()
+        self.dense = nn.Linear(i, o)
+
+
+class VideoMAELayer(_Holder):
+    def __init__(self, d, ff, eps):
+        super().__init__()
+        self.attention = VideoMAEAttention(d)
+        self.intermediate = _Dense(d, ff)
+        self.output = _Dense(ff, d)
+        self.layernorm_before = nn.LayerNorm(d, eps=eps)
+        self.layernorm_after = nn.LayerNorm(d, eps=eps)
+
+    def flat_params(self):
+        a = self.attention.attention
+        return (self.layernorm_before.weight, self.layernorm_before.bias, a.query.weight, a.key.weight, a.value.weight,
+                a.q_bias, a.v_bias, self.attention.output.dense.weight, self.attention.output.dense.bias,
+                self.layernorm_after.weight, self.layernorm_after.bias, self.intermediate.dense.weight,
+                self.intermediate.dense.bias, self.output.dense.weight, self.output.dense.bias)
+
+
+class VideoMAEEncoder(_Holder):
+    def __init__(self, c):
+        super().__init__()
+        self.layer = nn.ModuleList(VideoMAELayer(c.hidden_size, c.intermediate_size, c.layer_norm_eps)
+                                   for _ in range(c.num_hidden_layers))
+
+
+class VideoMAEModel(_Holder):
+    def __init__(self, c):
+        super().__init__()
+        self.embeddings = VideoMAEEmbeddings(c)
+        self.encoder = VideoMAEEncoder(c)
+        # use_mean_pooling=True -> no final LayerNorm (HF:415-418); the reference always sets it (pretrain_videomae.py:55)
+
+
+class VideoMAEDecoder(_Holder):
+    def __init__(self, c):
+        super().__init__()
+        self.decoder_layers = nn.ModuleList(
+            VideoMAELayer(c.decoder_hidden_size, c.decoder_intermediate_size, c.layer_norm_eps)
+            for _ in range(c.decoder_num_hidden_layers))
+        self.norm = nn.LayerNorm(c.decoder_hidden_size)  # eps 1e-5 (HF:497)
+        self.head = nn.Linear(c.decoder_hidden_size, c.num_channels * c.tubelet_size * c.patch_size ** 2)
+
+
+class VideoMAEForPreTraining(nn.Module):
+    """`model(pixel_values, bool_masked_pos=...) -> VideoMAEForPreTrainingOutput(loss, logits)`  (HF:540-680)."""
+
+    def __init__(self, config, output_logits: bool = True):
+        super().__init__()
+        c = config
+        if not getattr(c, "use_mean_pooling", True):
+            raise NotImplementedError("use_mean_pooling=False (final encoder LayerNorm) is not on the reference's path")
+        if getattr(c, "hidden_act", "gelu") != "gelu" or not getattr(c, "qkv_bias", True):
+            raise NotImplementedError("only hidden_act='gelu' and qkv_bias=True (the reference's configuration)")
+        if c.hidden_size % c.num_attention_heads or c.hidden_size // c.num_attention_heads != 64 or \
+                c.decoder_hidden_size // c.decoder_num_attention_heads != 64:
+            raise NotImplementedError("the sm_100a attention kernels are built for head_dim 64")
+        if c.num_channels != 3 or c.patch_size != 16 or c.tubelet_size not in (1, 2):
+            raise NotImplementedError("patchify kernel: 3 channels, 16x16 patches, tubelet 1 or 2")
+        self.config = c
+        self.output_logits = output_logits
+        self.videomae = VideoMAEModel(c)
+        self.encoder_to_decoder = nn.Linear(c.hidden_size, c.decoder_hidden_size, bias=False)
+        self.mask_token = nn.Parameter(torch.zeros(1, 1, c.decoder_hidden_size))
+        self.decoder = VideoMAEDecoder(c)
+        g = c.image_size // c.patch_size
+        self.num_patches = (c.num_frames // c.tubelet_size) * g * g
+        # fixed sin-cos tables: plain attributes, NOT buffers (absent from the state-dict, as in HF:104, HF:529)
+        self.position_embeddings_encoder = get_sinusoid_encoding_table(self.num_patches, c.hidden_size)
+        self.position_embeddings = get_sinusoid_encoding_table(self.num_patches, c.decoder_hidden_size)
+        self._pos_dev = {}
+        self._cache = Bf16Cache()
+        self._nv = None          # cached visible-token count (validated on device every step)
+        self._status = None      # device int32 flag: a mask row violated the equal-count contract
+        self._strict = os.environ.get("BVC_STRICT_MASK", "0") == "1"
+        self._init_weights(c.initializer_range)
+
+    # -- init: modeling_utils.py:2285-2325 (normal(0, initializer_range) weights, zero biases, LN 1/0) -------------
+    def _init_weights(self, std):
+        for m in self.modules():
+            if isinstance(m, (nn.Linear, nn.Conv3d)):
+                nn.init.normal_(m.weight, mean=0.0, std=std)
+                if m.bias is not None:
+                    nn.init.zeros_(m.bias)
+            elif isinstance(m, nn.LayerNorm):
+                nn.init.ones_(m.weight)
+                nn.init.zeros_(m.bias)
+            elif isinstance(m, VideoMAESelfAttention):
+                nn.init.zeros_(m.q_bias)
+                nn.init.zeros_(m.v_bias)
+        nn.init.zeros_(self.mask_token)
+
+    def _pos(self, dev):
+        t = self._pos_dev.get(dev)
+        if t is None:
+            t = (self.position_embeddings_encoder.to(dev).contiguous(), self.position_embeddings.to(dev).contiguous())
+            self._pos_dev[dev] = t
+        return t
+
+    def check_mask_status(self):
+        """Synchronise and raise if any forward since the last check saw rows with unequal mask counts."""
+        if self._status is not None and int(self._status.item()) != 0:
+            self._status.zero_()
+            raise ValueError("bool_masked_pos: every row must mask the same number of tokens (HF:121-122 reshape)")
+
+    # -- the hot path -------------------------------------------------------------------------------------------------
+    def forward(self, pixel_values, bool_masked_pos=None, **kwargs):
+        c = self.config
+        if pixel_values.dim() != 5:
+            raise ValueError("pixel_values must be [batch, frames, channels, height, width]")
+        B, T, C, H, W = pixel_values.shape
+        if C != c.num_channels:
+            raise ValueError("Make sure that the channel dimension of the pixel values match with the one set in the "
+                             "configuration.")  # HF:166-169
+        if H != c.image_size or W != c.image_size:
+            raise ValueError(f"Input image size ({H}*{W}) doesn't match model ({c.image_size}*{c.image_size}).")
+        if T != c.num_frames:
+            raise ValueError(f"expected {c.num_frames} frames, got {T}")
+        if bool_masked_pos is None:
+            raise ValueError("One must provided a boolean mask ")  # HF:582-583
+        if not pixel_values.is_cuda:
+            raise L.BvcError("VideoMAEForPreTraining (bvc-b200) runs on CUDA only; there is no CPU path")
+        dev = pixel_values.device
+        N = self.num_patches
+        if tuple(bool_masked_pos.shape) != (B, N):
+            raise ValueError(f"bool_masked_pos must be [{B}, {N}]")
+        x = pixel_values.detach()
+        if x.dtype != F32 or not x.is_contiguous():
+            x = x.to(F32).contiguous()
+        m = bool_masked_pos.to(device=dev)
+        m = (m if m.dtype == torch.bool else m != 0).contiguous().view(torch.uint8)
+
+        with torch.cuda.device(dev):
+            if self._status is None or self._status.device != dev:
+                self._status = torch.zeros(1, dtype=torch.int32, device=dev)
+            # visible-token count: read back once (or every step with BVC_STRICT_MASK=1), validated on device always
+            if self._nv is None or self._strict:
+                cnt = torch.empty(B, dtype=torch.int32, device=dev)
+                L.mask_count(m, cnt)
+                cnt = cnt.cpu()
+                if not bool((cnt == cnt[0]).all()):
+                    raise ValueError("bool_masked_pos: every row must mask the same number of tokens "
+                                     "(HF:121-122 reshape)")
+                self._nv = int(cnt[0])
+            nv = self._nv
+            nm = N - nv
+            if nv == 0 or nm == 0:
+                raise ValueError("bool_masked_pos must leave at least one visible and one masked token")
+
+            st = StepState(self._cache)
+            st.B, st.N, st.nv, st.nm, st.status = B, N, nv, nm, self._status
+            st.vis_idx = torch.zeros((B, nv), dtype=torch.int32, device=dev)
+            st.msk_idx = torch.zeros((B, nm), dtype=torch.int32, device=dev)
+            st.slot = torch.empty((B, N), dtype=torch.int32, device=dev)
+            L.mask_to_index(m, nv, st.vis_idx, st.msk_idx, st.slot, st.status)
+
+            K = C * c.tubelet_size * c.patch_size ** 2
+            patches = torch.empty((B * nv, K), dtype=BF16, device=dev)
+            target = torch.empty((B * nm, K), dtype=F32, device=dev)
+            L.patchify_target(x, st.slot, c.tubelet_size, c.patch_size, nv, patches, target,
+                              bool(getattr(c, "norm_pix_loss", True)))
+
+            pos_e, pos_d = self._pos(dev)
+            proj = self.videomae.embeddings.patch_embeddings.projection
+            h = EmbedFn.apply(proj.weight, proj.bias, patches, pos_e, st, "pe")
+            for i, layer in enumerate(self.videomae.encoder.layer):
+                h = BlockFn.apply(h, *layer.flat_params(), st, f"e{i}.", B, nv, c.num_attention_heads,
+                                  float(c.layer_norm_eps))
+            xf = EncToDecFn.apply(h, self.encoder_to_decoder.weight, self.mask_token, pos_d, st, "e2d")
+            for j, layer in enumerate(self.decoder.decoder_layers):
+                xf = BlockFn.apply(xf, *layer.flat_params(), st, f"d{j}.", B, N, c.decoder_num_attention_heads,
+                                   float(c.layer_norm_eps))
+            loss = HeadLossFn.apply(xf, self.decoder.norm.weight, self.decoder.norm.bias, self.decoder.head.weight,
+                                    self.decoder.head.bias, target, st, "head", self.output_logits)
+            logits = st.logits.view(B, nm, K) if st.logits is not None else None
+            st.logits = None
+        return VideoMAEForPreTrainingOutput(loss=loss, logits=logits)

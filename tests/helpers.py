@@ -1,0 +1,53 @@
+"""Shared helpers for the GPU parity tests: run the bvc model and the CPU oracle on identical seeded inputs."""
+import numpy as np
+import torch
+
+from oracle import videomae_oracle as O
+
+
+def bvc_config(cfg: O.OracleConfig):
+    import bvc_b200 as bvc
+    return bvc.VideoMAEConfig(
+        image_size=cfg.image_size, patch_size=cfg.patch_size, num_channels=cfg.num_channels,
+        num_frames=cfg.num_frames, tubelet_size=cfg.tubelet_size, hidden_size=cfg.hidden_size,
+        num_hidden_layers=cfg.num_hidden_layers, num_attention_heads=cfg.num_attention_heads,
+        intermediate_size=cfg.intermediate_size, decoder_num_attention_heads=cfg.decoder_num_attention_heads,
+        decoder_hidden_size=cfg.decoder_hidden_size, decoder_num_hidden_layers=cfg.decoder_num_hidden_layers,
+        decoder_intermediate_size=cfg.decoder_intermediate_size, layer_norm_eps=cfg.layer_norm_eps,
+        norm_pix_loss=cfg.norm_pix_loss)
+
+
+def run_bvc(cfg, params, x, mask, grad_scale=1.0, device="cuda:0"):
+    """loss, logits, grads of the CUDA path for a state-dict / inputs given as CPU tensors."""
+    import bvc_b200 as bvc
+    model = bvc.VideoMAEForPreTraining(bvc_config(cfg))
+    model.load_state_dict(params, strict=True)
+    model = model.to(device).train()
+    with torch.autocast("cuda", dtype=torch.bfloat16):  # the reference wraps the call in autocast (:306-308)
+        out = model(x.to(device), bool_masked_pos=mask.to(device))
+    (out.loss * grad_scale).backward()
+    torch.cuda.synchronize()
+    grads = {k: p.grad.detach().float().cpu() for k, p in model.named_parameters()}
+    missing = [k for k, p in model.named_parameters() if p.grad is None]
+    assert not missing, missing
+    return out.loss.detach().float().cpu(), out.logits.detach().float().cpu(), grads, model
+
+
+def rel_l2(a, b):
+    a, b = a.double().flatten(), b.double().flatten()
+    return float((a - b).norm() / max(float(b.norm()), 1e-30))
+
+
+def grad_report(grads, ref):
+    """per-tensor (rel-L2 error, rel norm error) and the global figures."""
+    rows = {}
+    num = den = 0.0
+    for k, r in ref.items():
+        g = grads[k].double()
+        r = r.double() if torch.is_tensor(r) else torch.from_numpy(np.asarray(r)).double()
+        e = float((g - r).norm())
+        n = float(r.norm())
+        rows[k] = (e / max(n, 1e-30), abs(float(g.norm()) - n) / max(n, 1e-30), n)
+        num += e * e
+        den += n * n
+    return rows, (num / max(den, 1e-60)) ** 0.5

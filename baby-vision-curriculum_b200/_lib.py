@@ -102,6 +102,33 @@ def _check(rc, what):
 
 
 _launches = 0
+_prof = None  # when a list: (kind, flops, bytes, start_event, end_event) per call, recorded on the current stream
+
+
+def set_profiler(records):
+    """bench.py: pass a list to time every libbvc.so call with CUDA events on its own stream; None to stop."""
+    global _prof
+    _prof = records
+
+
+class _Timed:
+    __slots__ = ("kind", "flops", "bytes", "s", "detail")
+
+    def __init__(self, kind, flops=0.0, nbytes=0.0, detail=""):
+        self.kind, self.flops, self.bytes, self.detail = kind, flops, nbytes, detail
+
+    def __enter__(self):
+        if _prof is not None:
+            self.s = torch.cuda.Event(enable_timing=True)
+            self.s.record()
+        return self
+
+    def __exit__(self, *exc):
+        if _prof is not None and exc[0] is None:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            _prof.append((self.kind, self.flops, self.bytes, self.s, e, self.detail))
+        return False
 
 
 def launch_count():
@@ -124,23 +151,26 @@ def _cuda(*ts):
 def mask_count(mask_u8, n_visible):
     _cuda(mask_u8, n_visible)
     B, N = mask_u8.shape
-    _check(load().bvc_mask_count(_p(mask_u8), B, N, _p(n_visible), _stream()), "bvc_mask_count")
+    with _Timed("mask", 0.0, float(B * N)):
+        _check(load().bvc_mask_count(_p(mask_u8), B, N, _p(n_visible), _stream()), "bvc_mask_count")
     _count()
 
 
 def mask_to_index(mask_u8, nv, vis_idx, msk_idx, slot, status):
     _cuda(mask_u8, vis_idx, msk_idx, slot, status)
     B, N = mask_u8.shape
-    _check(load().bvc_mask_to_index(_p(mask_u8), B, N, nv, _p(vis_idx), _p(msk_idx), _p(slot), _p(status), _stream()),
-           "bvc_mask_to_index")
+    with _Timed("mask", 0.0, float(B * N * 9)):
+        _check(load().bvc_mask_to_index(_p(mask_u8), B, N, nv, _p(vis_idx), _p(msk_idx), _p(slot), _p(status), _stream()),
+               "bvc_mask_to_index")
     _count()
 
 
 def patchify_target(pixels, slot, ts, ps, nv, patches_vis, target, norm_pix=True):
     _cuda(pixels, slot, patches_vis, target)
     B, T, Cc, H, W = pixels.shape
-    _check(load().bvc_patchify_target(_p(pixels), _p(slot), B, T, Cc, H, W, ts, ps, nv, _p(patches_vis), _p(target),
-                                      1 if norm_pix else 0, _stream()), "bvc_patchify_target")
+    with _Timed("patchify_target", 0.0, float(pixels.numel() * 4 + patches_vis.numel() * 2 + target.numel() * 4)):
+        _check(load().bvc_patchify_target(_p(pixels), _p(slot), B, T, Cc, H, W, ts, ps, nv, _p(patches_vis), _p(target),
+                                          1 if norm_pix else 0, _stream()), "bvc_patchify_target")
     _count()
 
 
@@ -175,7 +205,14 @@ def gemm(a, b, M, N, K, *, lda=None, ldb=None, a_mn=False, b_mn=False, out_f32=N
     g.loss_partial = loss_partial.data_ptr() if loss_partial is not None else None
     g.logits_out = logits_out.data_ptr() if logits_out is not None else None
     g.block_n = block_n
-    _check(load().bvc_gemm_bf16(C.byref(g), _stream()), "bvc_gemm_bf16")
+    detail = ""
+    if _prof is not None:
+        detail = (f"M{M} N{N} K{K} {'T' if a_mn else 'N'}{'T' if b_mn else 'N'}"
+                  f"{' gelu' if act == 1 else ' dgelu' if act == 2 else ''}{' res' if res is not None else ''}"
+                  f"{' loss' if target is not None else ''}{' f32' if out_f32 is not None else ''}"
+                  f"{' bf16' if out_bf16 is not None else ''}{' splitk' if k_splits != 1 else ''}")
+    with _Timed("gemm", 2.0 * M * N * K, 0.0, detail):
+        _check(load().bvc_gemm_bf16(C.byref(g), _stream()), "bvc_gemm_bf16")
     _count()
 
 
@@ -185,62 +222,71 @@ def gemm_loss_slots(M, N, block_n=0):
 
 def loss_finalize(partials, numel, status, loss):
     _cuda(partials, loss)
-    _check(load().bvc_loss_finalize(_p(partials), partials.numel(), float(numel), _p(status), _p(loss), _stream()),
-           "bvc_loss_finalize")
+    with _Timed("loss_finalize", 0.0, float(partials.numel() * 4)):
+        _check(load().bvc_loss_finalize(_p(partials), partials.numel(), float(numel), _p(status), _p(loss), _stream()),
+               "bvc_loss_finalize")
     _count()
 
 
 def layernorm_fwd(x, gamma, beta, eps, M, d, y, mean, rstd, ldx=None, seg=(0, 0, 0)):
     _cuda(x, gamma, beta, y, mean, rstd)
-    _check(load().bvc_layernorm_fwd(_p(x), ldx if ldx is not None else d, seg[0], seg[1], seg[2], _p(gamma), _p(beta),
-                                    eps, M, d, _p(y), _p(mean), _p(rstd), _stream()), "bvc_layernorm_fwd")
+    with _Timed("layernorm_fwd", 0.0, float(M) * d * 6):
+        _check(load().bvc_layernorm_fwd(_p(x), ldx if ldx is not None else d, seg[0], seg[1], seg[2], _p(gamma), _p(beta),
+                                        eps, M, d, _p(y), _p(mean), _p(rstd), _stream()), "bvc_layernorm_fwd")
     _count()
 
 
 def layernorm_bwd(dy, x, mean, rstd, gamma, dres, M, d, dx_f32, dx_bf16, dgamma, dbeta, ldx=None, seg=(0, 0, 0)):
     _cuda(dy, x, mean, rstd, gamma, dgamma, dbeta)
-    _check(load().bvc_layernorm_bwd(_p(dy), _p(x), ldx if ldx is not None else d, seg[0], seg[1], seg[2], _p(mean),
-                                    _p(rstd), _p(gamma), _p(dres), M, d, _p(dx_f32), _p(dx_bf16), _p(dgamma),
-                                    _p(dbeta), _stream()), "bvc_layernorm_bwd")
+    with _Timed("layernorm_bwd", 0.0, float(M) * d * (2 + 4 + (4 if dres is not None else 0) + (4 if dx_f32 is not None else 0) + (2 if dx_bf16 is not None else 0)), f"M{M} d{d}"):
+        _check(load().bvc_layernorm_bwd(_p(dy), _p(x), ldx if ldx is not None else d, seg[0], seg[1], seg[2], _p(mean),
+                                        _p(rstd), _p(gamma), _p(dres), M, d, _p(dx_f32), _p(dx_bf16), _p(dgamma),
+                                        _p(dbeta), _stream()), "bvc_layernorm_bwd")
     _count()
 
 
 def colsum(inp, M, N, out, ld=None, seg=(0, 0, 0), scale=1.0, scale_dev=None):
     _cuda(inp, out)
     is_f32 = 1 if inp.dtype == torch.float32 else 0
-    _check(load().bvc_colsum(_p(inp), is_f32, ld if ld is not None else N, seg[0], seg[1], seg[2], M, N, scale,
-                             _p(scale_dev), _p(out), _stream()), "bvc_colsum")
+    with _Timed("colsum", 0.0, float(M) * N * inp.element_size(), f"M{M} N{N}"):
+        _check(load().bvc_colsum(_p(inp), is_f32, ld if ld is not None else N, seg[0], seg[1], seg[2], M, N, scale,
+                                 _p(scale_dev), _p(out), _stream()), "bvc_colsum")
     _count()
 
 
 def cast_bf16(src, dst):
     _cuda(src, dst)
-    _check(load().bvc_cast_f32_to_bf16(_p(src), _p(dst), src.numel(), _stream()), "bvc_cast_f32_to_bf16")
+    with _Timed("cast", 0.0, float(src.numel()) * 6):
+        _check(load().bvc_cast_f32_to_bf16(_p(src), _p(dst), src.numel(), _stream()), "bvc_cast_f32_to_bf16")
     _count()
 
 
 def rows_to_bf16(src, M, d, dst, ld=None, seg=(0, 0, 0)):
     _cuda(src, dst)
-    _check(load().bvc_rows_to_bf16(_p(src), ld if ld is not None else d, seg[0], seg[1], seg[2], M, d, _p(dst),
-                                   _stream()), "bvc_rows_to_bf16")
+    with _Timed("rows_to_bf16", 0.0, float(M) * d * 6):
+        _check(load().bvc_rows_to_bf16(_p(src), ld if ld is not None else d, seg[0], seg[1], seg[2], M, d, _p(dst),
+                                       _stream()), "bvc_rows_to_bf16")
     _count()
 
 
 def decoder_mask_rows(x, mask_token, pos, msk_idx, B, N, nv, d):
     _cuda(x, mask_token, pos, msk_idx)
-    _check(load().bvc_decoder_mask_rows(_p(x), _p(mask_token), _p(pos), _p(msk_idx), B, N, nv, d, _stream()),
-           "bvc_decoder_mask_rows")
+    with _Timed("decoder_mask_rows", 0.0, float(B) * (N - nv) * d * 8):
+        _check(load().bvc_decoder_mask_rows(_p(x), _p(mask_token), _p(pos), _p(msk_idx), B, N, nv, d, _stream()),
+               "bvc_decoder_mask_rows")
     _count()
 
 
 def attn_fwd(qkv, B, S, H, scale, out, lse):
     _cuda(qkv, out, lse)
-    _check(load().bvc_attn_fwd(_p(qkv), B, S, H, scale, _p(out), _p(lse), _stream()), "bvc_attn_fwd")
+    with _Timed("attn_fwd", 4.0 * B * H * S * S * 64, 0.0, f"B{B} S{S} H{H}"):
+        _check(load().bvc_attn_fwd(_p(qkv), B, S, H, scale, _p(out), _p(lse), _stream()), "bvc_attn_fwd")
     _count()
 
 
 def attn_bwd(qkv, out, dout, lse, B, S, H, scale, delta, dqkv):
     _cuda(qkv, out, dout, lse, delta, dqkv)
-    _check(load().bvc_attn_bwd(_p(qkv), _p(out), _p(dout), _p(lse), B, S, H, scale, _p(delta), _p(dqkv), _stream()),
-           "bvc_attn_bwd")
-    _count(2)
+    with _Timed("attn_bwd", 8.0 * B * H * S * S * 64, 0.0, f"B{B} S{S} H{H}"):
+        _check(load().bvc_attn_bwd(_p(qkv), _p(out), _p(dout), _p(lse), B, S, H, scale, _p(delta), _p(dqkv), _stream()),
+               "bvc_attn_bwd")
+    _count(3)

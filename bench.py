@@ -1,0 +1,380 @@
+#!/usr/bin/env python
+"""bench.py -- VideoMAE ViT-B/16 pretraining step throughput (clips/s) on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config base] [--batch 64]
+
+A "step" is the body of the reference's hot loop (pretraining/generative/pretrain_videomae.py:292-314) on one batch
+of synthetic 16x224x224 clips with tube masks (ratio 0.9): forward + loss (+ the scalar-loss AllReduce of
+ddputils.py:53-68) + backward (DDP gradient all-reduce over NCCL for N > 1) + GradScaler step of SGD-nesterov
+(slurmscripts/generative/slurm_dev_def.bash) -- nothing skipped.  One process per GPU (torchrun for N > 1).
+
+value : whole-job clips/s with the clips and masks already resident in HBM (a 616 MB fp32 clip batch per GPU,
+        > the 126 MB L2, re-read from HBM every step).
+e2e   : the same loop through the public API from HOST buffers: every step copies its fp32 clip batch and bool mask
+        from pinned host memory (prefetched one step ahead on a copy stream) and reads the loss back to the host.
+roofline     : per-kernel CUDA-event timing of every libbvc.so launch inside the timed steps (bvc_b200._lib profiler).
+cpu_baseline : the reference's own CPU path (HF transformers VideoMAEForPreTraining, fp32) on this box's host cores,
+               bounded sample.   --impl reference prints that as its own line.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CONFIGS = {
+    "base": dict(hidden_size=768, num_hidden_layers=12, num_attention_heads=12, intermediate_size=3072,
+                 decoder_num_attention_heads=6, decoder_hidden_size=384, decoder_num_hidden_layers=4,
+                 decoder_intermediate_size=1536),
+    "small": dict(hidden_size=384, num_hidden_layers=12, num_attention_heads=6, intermediate_size=1536,
+                  decoder_num_attention_heads=3, decoder_hidden_size=192, decoder_num_hidden_layers=4,
+                  decoder_intermediate_size=768),
+    "large": dict(hidden_size=1024, num_hidden_layers=24, num_attention_heads=16, intermediate_size=4096,
+                  decoder_num_attention_heads=8, decoder_hidden_size=512, decoder_num_hidden_layers=4,
+                  decoder_intermediate_size=2048),
+}
+GRID = (8, 14, 14)
+MASK_RATIO = 0.9
+
+
+def flops_per_clip(c, nv=160, n=1568, k=1536):
+    """BASELINE.md section 3 convention: GEMM 2MNK, attention 4 S^2 d_h per head, backward = 2x forward (the
+    patch embedding has no dX), visible-only patch embedding, no recompute credit."""
+    def block(s, d, ff):
+        return 2 * s * d * (3 * d) + 2 * s * d * d + 2 * 2 * s * d * ff + 4 * s * s * d
+    d, dd = c["hidden_size"], c["decoder_hidden_size"]
+    pe = 2 * nv * k * d
+    rest = (c["num_hidden_layers"] * block(nv, d, c["intermediate_size"]) + 2 * nv * d * dd +
+            c["decoder_num_hidden_layers"] * block(n, dd, c["decoder_intermediate_size"]) + 2 * (n - nv) * dd * k)
+    return 2 * pe + 3 * rest
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return dict(hbm=d["hbm_gbs"], tc_burst=d["bf16_tflops"], tc=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    src="measured")
+    return dict(hbm=6650.0, tc_burst=1590.0, tc=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
+                                         text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def make_masks(batch, seed):
+    import bvc_b200 as bvc
+    np.random.seed(seed)
+    return bvc.batch_masks(bvc.TubeMaskingGenerator(GRID, MASK_RATIO), batch)
+
+
+# ====================================================================================================== reference arm
+def cpu_reference(cfg_name, batch, steps, warmup):
+    """The reference's CPU path: HF VideoMAEForPreTraining (the arithmetic behind pretrain_videomae.py:301) + SGD,
+    fp32, all host threads.  Falls back to the oracle port when transformers is not importable."""
+    cores = len(os.sched_getaffinity(0))
+    torch.set_num_threads(cores)
+    c = CONFIGS[cfg_name]
+    kind = "reference"
+    try:
+        import transformers
+        hfc = transformers.VideoMAEConfig(image_size=224, patch_size=16, num_channels=3, num_frames=16, tubelet_size=2,
+                                          initializer_range=0.02, use_mean_pooling=True, norm_pix_loss=True, **c)
+        torch.manual_seed(0)
+        model = transformers.VideoMAEForPreTraining(hfc).train()
+        opt = torch.optim.SGD(model.parameters(), lr=0.1, momentum=0.9, nesterov=True)
+
+        def step(x, m):
+            opt.zero_grad()
+            loss = model(x, bool_masked_pos=m).loss
+            loss.backward()
+            opt.step()
+            return float(loss.detach())
+    except Exception:  # noqa: BLE001
+        from oracle import videomae_oracle as O
+        kind = "port"
+        ocfg = O.make_config(cfg_name)
+        params = {k: v.requires_grad_(True) for k, v in O.init_params(ocfg, 0).items()}
+        opt = torch.optim.SGD(list(params.values()), lr=0.1, momentum=0.9, nesterov=True)
+
+        def step(x, m):
+            opt.zero_grad()
+            loss, _ = O.forward_loss(params, x, m, ocfg)
+            loss.backward()
+            opt.step()
+            return float(loss.detach())
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(batch, 16, 3, 224, 224, generator=g)
+    times = []
+    for i in range(warmup + steps):
+        m = make_masks(batch, i)
+        t0 = time.perf_counter()
+        step(x, m)
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    dt = sum(times) / len(times)
+    return {"value": batch / dt, "unit": "clips/s", "cores": cores, "kind": kind, "ms_per_step": dt * 1e3,
+            "sample": f"{steps} steps (after {warmup} warm-up) of VideoMAE ViT-{cfg_name} fwd+bwd+SGD at batch {batch}, "
+                      f"fp32, 16x224x224 synthetic clips, tube mask 0.9, torch {torch.__version__} CPU threads={cores}"}
+
+
+# ====================================================================================================== our arm
+def run_ours(args):
+    import torch.distributed as dist
+    import bvc_b200 as bvc
+    from bvc_b200 import _lib as L
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    c = CONFIGS[args.config]
+    B = args.batch
+    torch.manual_seed(0)
+    model = bvc.VideoMAEForPreTraining(bvc.VideoMAEConfig(**c)).to(dev).train()
+    xmodel = model
+    if world > 1:
+        xmodel = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], output_device=local,
+                                                           find_unused_parameters=False)
+    opt = torch.optim.SGD(xmodel.parameters(), lr=0.1, momentum=0.9, nesterov=True)
+    scaler = torch.amp.GradScaler("cuda")
+
+    n_pool = 2
+    g = torch.Generator().manual_seed(1234 + rank)
+    host_clips = [torch.randn(B, 16, 3, 224, 224, generator=g).pin_memory() for _ in range(n_pool)]
+    host_masks = [make_masks(B, 100 * rank + i).pin_memory() for i in range(8)]
+    dev_clips = [t.to(dev) for t in host_clips]
+    dev_masks = [t.to(dev) for t in host_masks]
+
+    def train_step(x, m):
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            opt.zero_grad()
+            loss = xmodel(x, bool_masked_pos=m).loss
+            loss = bvc.AllReduce.apply(loss)
+        scaler.scale(loss).backward()
+        scaler.step(opt)
+        scaler.update()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ------------------------------------------------------------------ resident-input loop (value)
+    for i in range(args.warmup):
+        train_step(dev_clips[i % n_pool], dev_masks[i % 8])
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    records = []
+    L.set_profiler(records)
+    n0 = L.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        loss = train_step(dev_clips[i % n_pool], dev_masks[i % 8])
+    e1.record()
+    barrier()
+    L.set_profiler(None)
+    launches = L.launch_count() - n0
+    clocks = sampler.stop() if rank == 0 else None
+    ms = e0.elapsed_time(e1)
+    last_loss = float(loss.detach())
+
+    # ------------------------------------------------------------------ host-buffer loop (e2e)
+    copy_stream = torch.cuda.Stream(device=dev)
+    stage = [(torch.empty_like(dev_clips[0]), torch.empty_like(dev_masks[0])) for _ in range(2)]
+    loss_host = torch.zeros(1).pin_memory()
+
+    def prefetch(i):
+        buf = stage[i % 2]
+        with torch.cuda.stream(copy_stream):
+            buf[0].copy_(host_clips[i % n_pool], non_blocking=True)
+            buf[1].copy_(host_masks[i % 8], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        return ev
+
+    def e2e_loop(n):
+        ev = prefetch(0)
+        for i in range(n):
+            torch.cuda.current_stream().wait_event(ev)
+            x, m = stage[i % 2]
+            if i + 1 < n:
+                # the other staging buffer was last read by step i-1, already ordered before this point on the
+                # compute stream; make the copy stream wait for it
+                copy_stream.wait_stream(torch.cuda.current_stream())
+                ev = prefetch(i + 1)
+            loss = train_step(x, m)
+            loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
+            torch.cuda.current_stream().synchronize()  # the step's loss is on the host (what the reference logs)
+        return float(loss_host)
+
+    e2e_loop(max(2, args.warmup // 2))
+    barrier()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    e2e_loop(args.steps)
+    t1.record()
+    barrier()
+    ms_e2e = t0.elapsed_time(t1)
+
+    t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = float(t[0]), float(t[1])
+
+    if rank == 0:
+        peaks = measured_peaks()
+        torch.cuda.synchronize()
+        agg = {}
+        detail = {}
+        for kind, fl, by, s, e, dt in records:
+            if dt:
+                dd = detail.setdefault(kind + ' ' + dt, [0, 0.0, 0.0])
+                dd[0] += 1
+                dd[1] += s.elapsed_time(e)
+                dd[2] += fl if fl > 0 else by
+            a = agg.setdefault(kind, [0, 0.0, 0.0, 0.0])
+            a[0] += 1
+            a[1] += s.elapsed_time(e)
+            a[2] += fl
+            a[3] += by
+        total_kernel_ms = sum(a[1] for a in agg.values())
+        kernels = []
+        for kind, (n, kms, fl, by) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+            tensor = fl > 0
+            ach = (fl / kms / 1e9) if tensor else (by / kms / 1e6)
+            peak = peaks["tc"] if tensor else peaks["hbm"]
+            kernels.append({"kernel": kind, "bound": "tensor" if tensor else "hbm", "launches_per_step": n / args.steps,
+                            "ms_per_step": kms / args.steps, "share_of_kernel_time": kms / total_kernel_ms,
+                            "achieved": ach, "peak": peak, "unit": "TFLOP/s" if tensor else "GB/s", "frac": ach / peak})
+        top = dict(kernels[0])
+        roof = {"bound": top["bound"], "achieved": top["achieved"], "peak": top["peak"], "unit": top["unit"],
+                "frac": top["frac"], "traffic": None, "kernel": top["kernel"],
+                "peak_source": f"MEASURED_PEAKS.json ({peaks['src']}; sustained bf16 figure: kernel timed inside a long step)",
+                "share_of_step": top["ms_per_step"] / (ms / args.steps)}
+        step_flops = flops_per_clip(c) * B
+        cpu = cpu_reference(args.config, args.cpu_batch, args.cpu_steps, 1) if not args.no_cpu else None
+        clips = B * world
+        out = {
+            "metric": "VideoMAE ViT-B/16 pretrain clips/s" if args.config == "base" else f"VideoMAE ViT-{args.config} clips/s",
+            "value": clips * args.steps / (ms / 1e3), "unit": "clips/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"VideoMAE ViT-{args.config[0].upper()}/16 pretraining step (fwd+loss+bwd+DDP allreduce+"
+                                   f"GradScaler/SGD-nesterov), 16x224x224 clips, tube mask 0.9, batch {B}/GPU",
+                       "global_batch": clips, "parallelism": f"dp{world}", "l2": "inputs larger than L2 "
+                       "(616 MB clip batch per step, alternating between two resident batches)"},
+            "model_tflops_per_gpu": step_flops / (ms / args.steps) / 1e9,
+            "model_tc_frac": step_flops / (ms / args.steps) / 1e9 / peaks["tc"],
+            "e2e": {"value": clips * args.steps / (ms_e2e / 1e3), "unit": "clips/s",
+                    "h2d_bytes_per_step": host_clips[0].numel() * 4 + host_masks[0].numel(),
+                    "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches, "roofline": roof, "kernels": kernels, "cpu_baseline": cpu, "clocks": clocks,
+            "loss_last": last_loss,
+        }
+        print(json.dumps(out))
+        if args.detail:
+            rows = [{"what": k, "launches_per_step": v[0] / args.steps, "ms_per_step": v[1] / args.steps,
+                     "rate": v[2] / v[1] / 1e9 if v[1] > 0 else 0.0} for k, v in detail.items()]
+            rows.sort(key=lambda r: -r["ms_per_step"])
+            with open(args.detail, "w") as f:
+                json.dump(rows, f, indent=1)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    r = cpu_reference(args.config, args.cpu_batch, max(1, args.steps), max(1, min(args.warmup, 1)))
+    out = {"impl": "reference", "metric": "VideoMAE ViT-B/16 pretrain clips/s", "value": r["value"], "unit": "clips/s",
+           "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": f"VideoMAE ViT-{args.config[0].upper()}/16 pretraining step on the host CPU "
+                                  f"(bounded sample: batch {args.cpu_batch})", "global_batch": args.cpu_batch,
+                      "parallelism": "cpu"},
+           "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+           "e2e": {"value": r["value"], "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="base", choices=sorted(CONFIGS))
+    ap.add_argument("--batch", type=int, default=64)
+    ap.add_argument("--cpu-batch", type=int, default=4)
+    ap.add_argument("--cpu-steps", type=int, default=3)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--detail", default="", help="write a per-shape kernel time breakdown (JSON) to this path")
+    a = ap.parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -1,0 +1,107 @@
+"""CPU-side checks (no GPU): the C-ABI library loads and exports every symbol include/bvc.h declares, the host-side
+mirrors of the reference interface behave like the reference, and the product path refuses to run without CUDA."""
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import videomae_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def bvc():
+    import __graft_entry__ as g
+    g.build()
+    import bvc_b200
+    return bvc_b200
+
+
+def test_library_exports_every_declared_symbol(bvc):
+    hdr = open(os.path.join(ROOT, "include", "bvc.h")).read()
+    declared = set(re.findall(r"\b(bvc_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    lib = bvc._lib.load()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert declared == set(bvc._lib.EXPORTED_SYMBOLS)
+    assert lib.bvc_abi_version() == bvc._lib.ABI_VERSION
+    # host-only entry point: tile bookkeeping of the fused loss epilogue
+    assert lib.bvc_gemm_loss_slots(256, 512, 256) == 2 * 2 * 8
+
+
+def test_masking_mirror_matches_reference_fixtures(bvc, golden_dir):
+    g = np.load(os.path.join(golden_dir, "masks.npz"))
+    np.random.seed(0)
+    gen = bvc.TubeMaskingGenerator((8, 14, 14), 0.9)
+    got = np.stack([gen() for _ in range(4)]).astype(np.uint8)
+    assert np.array_equal(got, g["tube_8x14x14_r90"])
+    assert gen.total_masks == 1408 and gen.num_masks_per_frame == 176 and "mask patches 1408" in repr(gen)
+    np.random.seed(0)
+    rg = bvc.RandomMaskingGenerator((8, 14, 14), 0.9)
+    assert np.array_equal(np.stack([rg() for _ in range(2)]).astype(np.uint8), g["random_8x14x14_r90"])
+    np.random.seed(5)
+    m = bvc.batch_masks(bvc.TubeMaskingGenerator((8, 14, 14), 0.9), 3)
+    assert m.dtype == torch.bool and m.shape == (3, 1568) and bool((m.sum(1) == 1408).all())
+
+
+def test_module_matches_hf_state_dict_contract(bvc):
+    for name in ("tiny", "small", "base"):
+        cfg = O.make_config(name)
+        from tests.helpers import bvc_config
+        m = bvc.VideoMAEForPreTraining(bvc_config(cfg))
+        shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+        assert shapes == {k: tuple(s) for k, s in O.param_shapes(cfg).items()}
+        assert not list(m.buffers())  # sinusoid tables are plain attributes, as in HF
+        assert m.config.image_size == cfg.image_size and m.config.tubelet_size == cfg.tubelet_size
+        # HF init: zero biases / mask_token / q_bias / v_bias, unit LayerNorm, N(0, 0.02) weights
+        sd = m.state_dict()
+        assert float(sd["mask_token"].abs().max()) == 0.0
+        assert float(sd["decoder.head.bias"].abs().max()) == 0.0
+        assert abs(float(sd["decoder.head.weight"].std()) - 0.02) < 2e-3
+        assert torch.equal(m.position_embeddings, O.sinusoid_table(cfg.seq_len, cfg.decoder_hidden_size))
+
+
+def test_hf_state_dict_loads_both_ways(bvc):
+    transformers = pytest.importorskip("transformers")
+    c = transformers.VideoMAEConfig(image_size=32, num_frames=4, hidden_size=64, num_hidden_layers=2,
+                                    num_attention_heads=1, intermediate_size=128, decoder_num_attention_heads=1,
+                                    decoder_hidden_size=64, decoder_num_hidden_layers=1,
+                                    decoder_intermediate_size=128, norm_pix_loss=True)
+    hf = transformers.VideoMAEForPreTraining(c)
+    ours = bvc.VideoMAEForPreTraining(c)  # a real transformers config object is accepted
+    ours.load_state_dict(hf.state_dict(), strict=True)
+    hf.load_state_dict(ours.state_dict(), strict=True)
+    assert [k for k, _ in ours.named_parameters()] == [k for k, _ in hf.named_parameters()]
+
+
+def test_no_cpu_fallback(bvc):
+    cfg = O.make_config("tiny")
+    from tests.helpers import bvc_config
+    m = bvc.VideoMAEForPreTraining(bvc_config(cfg))
+    x = O.synthetic_clip(1, cfg)
+    mask = torch.zeros(1, cfg.seq_len, dtype=torch.bool)
+    mask[:, :4] = True
+    with pytest.raises(ValueError):
+        m(x)  # mask is mandatory (HF:582-583) -- checked before any device work
+    with pytest.raises(bvc.BvcError):
+        m(x, bool_masked_pos=mask)
+    with pytest.raises(bvc.BvcError):
+        bvc._lib.cast_bf16(torch.zeros(8), torch.zeros(8, dtype=torch.bfloat16))
+
+
+def test_unsupported_configs_fail_loudly(bvc):
+    with pytest.raises(NotImplementedError):
+        bvc.VideoMAEForPreTraining(bvc.VideoMAEConfig(num_attention_heads=8))  # head_dim 96
+    with pytest.raises(NotImplementedError):
+        bvc.VideoMAEForPreTraining(bvc.VideoMAEConfig(use_mean_pooling=False))
+
+
+def test_bench_flop_model_matches_baseline_md():
+    import bench
+    assert abs(bench.flops_per_clip(bench.CONFIGS["base"]) / 1e9 - 202.3) < 0.5
+    assert abs(bench.flops_per_clip(bench.CONFIGS["small"]) / 1e9 - 64.0) < 0.5
+    assert abs(bench.flops_per_clip(bench.CONFIGS["large"]) / 1e9 - 484.4) < 1.0

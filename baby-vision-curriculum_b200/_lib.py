@@ -12,7 +12,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libbvc.so")
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 _lib = None
 
@@ -54,6 +54,7 @@ _SIGNATURES = {
     "bvc_colsum": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                              C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
     "bvc_cast_f32_to_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "bvc_cast_multi": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
     "bvc_rows_to_bf16": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                    C.c_void_p, C.c_void_p]),
     "bvc_decoder_mask_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
@@ -236,12 +237,13 @@ def layernorm_fwd(x, gamma, beta, eps, M, d, y, mean, rstd, ldx=None, seg=(0, 0,
     _count()
 
 
-def layernorm_bwd(dy, x, mean, rstd, gamma, dres, M, d, dx_f32, dx_bf16, dgamma, dbeta, ldx=None, seg=(0, 0, 0)):
+def layernorm_bwd(dy, x, mean, rstd, gamma, dres, M, d, dx_f32, dx_bf16, dgamma, dbeta, ldx=None, seg=(0, 0, 0),
+                  dxsum=None):
     _cuda(dy, x, mean, rstd, gamma, dgamma, dbeta)
     with _Timed("layernorm_bwd", 0.0, float(M) * d * (2 + 4 + (4 if dres is not None else 0) + (4 if dx_f32 is not None else 0) + (2 if dx_bf16 is not None else 0)), f"M{M} d{d}"):
         _check(load().bvc_layernorm_bwd(_p(dy), _p(x), ldx if ldx is not None else d, seg[0], seg[1], seg[2], _p(mean),
                                         _p(rstd), _p(gamma), _p(dres), M, d, _p(dx_f32), _p(dx_bf16), _p(dgamma),
-                                        _p(dbeta), _stream()), "bvc_layernorm_bwd")
+                                        _p(dbeta), _p(dxsum), _stream()), "bvc_layernorm_bwd")
     _count()
 
 
@@ -258,6 +260,13 @@ def cast_bf16(src, dst):
     _cuda(src, dst)
     with _Timed("cast", 0.0, float(src.numel()) * 6):
         _check(load().bvc_cast_f32_to_bf16(_p(src), _p(dst), src.numel(), _stream()), "bvc_cast_f32_to_bf16")
+    _count()
+
+
+def cast_multi(table, n_entries, total_elems):
+    _cuda(table)
+    with _Timed("cast", 0.0, float(total_elems) * 6):
+        _check(load().bvc_cast_multi(_p(table), n_entries, _stream()), "bvc_cast_multi")
     _count()
 
 

@@ -1,0 +1,5 @@
+// gemm_bn192.cu -- instantiations of the tcgen05 GEMM for 128 x 192 output tiles.
+#include "gemm_kernel.cuh"
+namespace bvc {
+int gemm_launch_bn192(const bvc_gemm_args* a, int epi, cudaStream_t s) { return gemm_dispatch_bn<192>(a, epi, s); }
+}  // namespace bvc

@@ -1,0 +1,469 @@
+// gemm_kernel.cuh -- the tcgen05 GEMM kernel template and its launcher (see gemm.cu for the overview).  Included by
+// one translation unit per tile width (gemm_bn*.cu) so that the instantiations compile in parallel.
+#pragma once
+#include "../../include/bvc.h"
+#include "bvc_host.h"
+#include "bvc_ptx.cuh"
+
+namespace bvc {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int kEpiWarps = 8;
+constexpr int kGemmThreads = 64 + kEpiWarps * 32;
+
+// compile-time epilogue variants: each instantiation carries only the code it needs (the all-runtime-flags epilogue
+// is ~56 KB of SASS and instruction-cache bound: ncu source view showed stall_no_inst on every flag test)
+enum GemmEpi { EPI_GENERIC = 0, EPI_PLAIN = 1, EPI_GELU = 2, EPI_DGELU = 3, EPI_RES = 4, EPI_SPLITK = 5, EPI_LOSS = 6 };
+
+struct GemmParams {
+  int M, N, K;
+  int k_splits, kb_total, kb_per_split;
+  int tiles_m, tiles_n;
+  float* out_f32;
+  bf16* out_bf16;
+  long long ldo;
+  int out_seg, out_seg_stride, out_seg_off;
+  float alpha;
+  const float* alpha_dev;
+  const float* bias;
+  int act;
+  bf16* aux_out;
+  const bf16* aux_in;
+  long long ld_aux;
+  const float* res;
+  long long ldr;
+  const int* res_idx;
+  const float* target;
+  long long ldt;
+  float* loss_partial;
+  bf16* logits_out;
+  int has_pre;  // tma_pre describes the epilogue's global operand (residual / target / GELU pre-activation)
+};
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int kABytes = BM * BK * 2;
+  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (BN == 256) ? 4 : (BN == 192) ? 4 : (BN == 128) ? 6 : 8;
+  static constexpr int kTmemCols = (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+  static constexpr int kStagingBytes = kEpiWarps * 4096;  // per epilogue warp: 32 rows x 32 fp32, 128B-swizzled
+  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+// Phi(-a) = 2^(-Q(a)) for a in [0, 6]: degree-7 minimax fit of Q(a) = -log2(Phi(-a)) (tools/fit_gelu.py); relative
+// error of Phi(-a) <= 3.3e-6 over the whole range (tails included), i.e. far below the bf16 rounding of the
+// activation that follows.  One MUFU.EX2 and 7 FMAs instead of erff().
+__device__ __forceinline__ float phi_neg_abs(float x) {
+  const float a = fminf(fabsf(x), 6.0f);
+  float q = -1.8348840982e-06f;
+  q = fmaf(q, a, 6.1599723096e-05f);
+  q = fmaf(q, a, -9.3053573547e-04f);
+  q = fmaf(q, a, 8.5079311974e-03f);
+  q = fmaf(q, a, -5.3960143443e-02f);
+  q = fmaf(q, a, -4.5846433058e-01f);
+  q = fmaf(q, a, -1.1512510639e+00f);
+  q = fmaf(q, a, -9.9999529365e-01f);
+  return exp2f(q);  // = Phi(-|x|)
+}
+// exact-erf GELU (HF:316, torch.nn.functional.gelu default): x * Phi(x)
+__device__ __forceinline__ float gelu_erf(float x) {
+  const float xw = x * phi_neg_abs(x);
+  return x > 0.f ? x - xw : xw;
+}
+__device__ __forceinline__ float gelu_erf_grad(float x) {
+  const float w = phi_neg_abs(x);
+  const float cdf = x > 0.f ? 1.0f - w : w;
+  const float pdf = 0.3989422804014327f * exp2f(-0.72134752044448170f * x * x);
+  return fmaf(x, pdf, cdf);
+}
+
+template <int BN, int A_MN, int B_MN, int EPI>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+            const __grid_constant__ CUtensorMap tma_pre, const __grid_constant__ GemmParams p) {
+  using Cfg = GemmCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* staging = smem + Cfg::kStages * Cfg::kStageBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + Cfg::kStagingBytes);
+  uint64_t* empty_bar = full_bar + Cfg::kStages;
+  uint64_t* tmem_full = empty_bar + Cfg::kStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tma_a);
+    tma_prefetch_desc(&tma_b);
+    for (int i = 0; i < Cfg::kStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], kEpiWarps);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int total_work = p.tiles_m * p.tiles_n * p.k_splits;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+        const int split = w % p.k_splits;
+        const int tile = w / p.k_splits;
+        const int m0 = (tile / p.tiles_n) * BM;
+        const int n0 = (tile % p.tiles_n) * BN;
+        const int kb0 = split * p.kb_per_split;
+        const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+        // pull this tile's epilogue operand into L2 while its MMAs run: the epilogue's loads then see L2 latency,
+        // not DRAM latency (the epilogue warps keep only ~4 KB each in flight)
+        if ((EPI == EPI_RES || EPI == EPI_LOSS || EPI == EPI_DGELU) && p.has_pre)
+          asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(
+                           reinterpret_cast<uint64_t>(&tma_pre)),
+                       "r"(n0), "r"(m0)
+                       : "memory");
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          uint8_t* sa = smem + stage * Cfg::kStageBytes;
+          uint8_t* sb = sa + Cfg::kABytes;
+          mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+          if (A_MN == 0) {
+            tma_load_2d(sa, &tma_a, &full_bar[stage], kb * BK, m0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BM / 64; ++j) tma_load_2d(sa + j * 8192, &tma_a, &full_bar[stage], m0 + j * 64, kb * BK);
+          }
+          if (B_MN == 0) {
+            tma_load_2d(sb, &tma_b, &full_bar[stage], kb * BK, n0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j) tma_load_2d(sb + j * 8192, &tma_b, &full_bar[stage], n0 + j * 64, kb * BK);
+          }
+          if (++stage == Cfg::kStages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BN, A_MN, B_MN, BM);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+        const int split = w % p.k_splits;
+        const int kb0 = split * p.kb_per_split;
+        const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + stage * Cfg::kStageBytes);
+          const uint32_t b_addr = a_addr + Cfg::kABytes;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t da = A_MN ? umma_smem_desc(a_addr + k * 2048, 1024, 8192)
+                                     : umma_smem_desc(a_addr + k * 32, 1024, 16);
+            const uint64_t db = B_MN ? umma_smem_desc(b_addr + k * 2048, 1024, 8192)
+                                     : umma_smem_desc(b_addr + k * 32, 1024, 16);
+            umma_bf16_ss(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == Cfg::kStages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        umma_commit(&tmem_full[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+    }
+  } else {
+    // ---------------------------------------------------------------- epilogue warps
+    // Phase 1: tcgen05.ld gives every lane one accumulator ROW (32 columns); the warp transposes the 32x32 fp32
+    // chunk through a 128B-swizzled staging buffer.  Phase 2: 8 lanes cover one row's 128 bytes, 4 rows per
+    // instruction, so every global access of the fused epilogue (residual, target, aux, outputs) is coalesced.
+    const int e = warp - 2;
+    const int q = warp & 3;          // TMEM lane quadrant this warp may read
+    const int half = e >> 2;         // which half of the BN columns
+    constexpr int kColsPerWarp = BN / 2;
+    uint8_t* stg = staging + e * 4096;
+    const int c4 = lane & 7;         // phase 2: this lane's 4-column group inside the 32-column chunk
+    const int rsub = lane >> 3;      // phase 2: row within each group of 4 rows
+    const float alpha = p.alpha * (p.alpha_dev ? __ldg(p.alpha_dev) : 1.0f);
+    constexpr bool G = EPI == EPI_GENERIC;
+    const bool kSplit = G ? p.k_splits > 1 : EPI == EPI_SPLITK;
+    const bool kGelu = G ? p.act == 1 : EPI == EPI_GELU;
+    const bool kDgelu = G ? p.act == 2 : EPI == EPI_DGELU;
+    const bool kRes = G ? p.res != nullptr : EPI == EPI_RES;
+    const bool kLoss = G ? p.target != nullptr : EPI == EPI_LOSS;
+    const bool kSeg = G || EPI == EPI_RES;
+    const bool kOutF32 = G ? p.out_f32 != nullptr : EPI == EPI_RES;
+    const bool kOutBf16 = G ? p.out_bf16 != nullptr : (EPI == EPI_PLAIN || EPI == EPI_GELU || EPI == EPI_DGELU ||
+                                                         EPI == EPI_LOSS);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+      const int tile = w / p.k_splits;
+      const int m0 = (tile / p.tiles_n) * BM;
+      const int n0 = (tile % p.tiles_n) * BN;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const int rbase = m0 + q * 32;
+      float lsum = 0.f;
+#pragma unroll 1
+      for (int cc = 0; cc < kColsPerWarp; cc += 32) {
+        const int c_tile = half * kColsPerWarp + cc;
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c_tile), v);
+        tmem_ld_wait();
+        if (cc + 32 >= kColsPerWarp) {  // last chunk of this tile is in registers: hand the accumulator back
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        }
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          *reinterpret_cast<uint4*>(stg + lane * 128 + ((c ^ (lane & 7)) << 4)) =
+              make_uint4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+        __syncwarp();
+        const int col = n0 + c_tile + c4 * 4;
+        if (col < p.N) {
+          float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (p.bias) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+          // global operands of the fused epilogue first, all 8 rows in flight at once (issuing them inside the
+          // row loop serialises one DRAM round trip per row: measured 5x slower on the residual / GELU' GEMMs)
+          float4 pre_f[8];
+          uint2 pre_h[8];
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int r = rbase + it * 4 + rsub;
+            pre_f[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+            pre_h[it] = make_uint2(0u, 0u);
+            if (r < p.M) {
+              if (kRes) {
+                const long long rr = p.res_idx ? (long long)__ldg(p.res_idx + r) : (long long)r;
+                pre_f[it] = __ldg(reinterpret_cast<const float4*>(p.res + rr * p.ldr + col));
+              } else if (kLoss) {
+                pre_f[it] = __ldg(reinterpret_cast<const float4*>(p.target + (long long)r * p.ldt + col));
+              }
+              if (kDgelu) pre_h[it] = __ldg(reinterpret_cast<const uint2*>(p.aux_in + (long long)r * p.ld_aux + col));
+            }
+          }
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int rl = it * 4 + rsub;
+            const int r = rbase + rl;
+            if (r >= p.M) continue;
+            const float4 t = *reinterpret_cast<const float4*>(stg + rl * 128 + ((c4 ^ (rl & 7)) << 4));
+            float x[4] = {t.x * alpha, t.y * alpha, t.z * alpha, t.w * alpha};
+            long long R = r;
+            if (kSeg && p.out_seg > 0)
+              R = (long long)(r / p.out_seg) * p.out_seg_stride + (r % p.out_seg) + p.out_seg_off;
+            if (kSplit) {
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p.out_f32 + R * p.ldo + col),
+                           "f"(x[0]), "f"(x[1]), "f"(x[2]), "f"(x[3])
+                           : "memory");
+              continue;
+            }
+            x[0] += bias4.x; x[1] += bias4.y; x[2] += bias4.z; x[3] += bias4.w;
+            if (kGelu) {
+              uint2 pk;
+              pk.x = pack_bf16x2(x[0], x[1]);
+              pk.y = pack_bf16x2(x[2], x[3]);
+              if (p.aux_out) *reinterpret_cast<uint2*>(p.aux_out + (long long)r * p.ld_aux + col) = pk;
+              x[0] = gelu_erf(__uint_as_float(pk.x << 16));
+              x[1] = gelu_erf(__uint_as_float(pk.x & 0xffff0000u));
+              x[2] = gelu_erf(__uint_as_float(pk.y << 16));
+              x[3] = gelu_erf(__uint_as_float(pk.y & 0xffff0000u));
+            } else if (kDgelu) {
+              const uint2 pk = pre_h[it];
+              x[0] *= gelu_erf_grad(__uint_as_float(pk.x << 16));
+              x[1] *= gelu_erf_grad(__uint_as_float(pk.x & 0xffff0000u));
+              x[2] *= gelu_erf_grad(__uint_as_float(pk.y << 16));
+              x[3] *= gelu_erf_grad(__uint_as_float(pk.y & 0xffff0000u));
+            }
+            if (kRes) {
+              const float4 rv = pre_f[it];
+              x[0] += rv.x; x[1] += rv.y; x[2] += rv.z; x[3] += rv.w;
+            }
+            if (kLoss) {
+              if (p.logits_out) {
+                uint2 pk;
+                pk.x = pack_bf16x2(x[0], x[1]);
+                pk.y = pack_bf16x2(x[2], x[3]);
+                *reinterpret_cast<uint2*>(p.logits_out + R * p.ldo + col) = pk;
+              }
+              const float4 tv = pre_f[it];
+              x[0] -= tv.x; x[1] -= tv.y; x[2] -= tv.z; x[3] -= tv.w;
+              lsum = fmaf(x[0], x[0], lsum); lsum = fmaf(x[1], x[1], lsum);
+              lsum = fmaf(x[2], x[2], lsum); lsum = fmaf(x[3], x[3], lsum);
+            }
+            if (kOutF32) *reinterpret_cast<float4*>(p.out_f32 + R * p.ldo + col) = make_float4(x[0], x[1], x[2], x[3]);
+            if (kOutBf16) {
+              uint2 pk;
+              pk.x = pack_bf16x2(x[0], x[1]);
+              pk.y = pack_bf16x2(x[2], x[3]);
+              *reinterpret_cast<uint2*>(p.out_bf16 + R * p.ldo + col) = pk;
+            }
+          }
+        }
+        __syncwarp();
+      }
+      if (kLoss && p.loss_partial) {
+        lsum = warp_sum(lsum);
+        if (lane == 0) p.loss_partial[(long long)tile * kEpiWarps + e] = lsum;
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+// k-split resolution shared by the host dispatcher (it decides the epilogue variant) and the launcher
+static inline void resolve_k_splits(const bvc_gemm_args* a, int bn, int* kb_per_split, int* k_splits) {
+  const int tiles_m = (a->M + BM - 1) / BM, tiles_n = (a->N + bn - 1) / bn;
+  const int kb_total = (a->K + BK - 1) / BK;
+  int ks = a->k_splits;
+  const int sms = num_sms();
+  if (ks <= 0) {
+    const long long tiles = (long long)tiles_m * tiles_n;
+    ks = (int)((2LL * sms + tiles - 1) / tiles);  // ~2 waves of work items
+    if (ks < 1) ks = 1;
+    if (ks > kb_total / 4) ks = kb_total / 4 > 0 ? kb_total / 4 : 1;  // >= 4 k-blocks per split
+  }
+  if (ks > kb_total) ks = kb_total;
+  *kb_per_split = (kb_total + ks - 1) / ks;
+  *k_splits = (kb_total + *kb_per_split - 1) / *kb_per_split;
+}
+
+template <int BN, int A_MN, int B_MN, int EPI>
+static int launch_gemm(const bvc_gemm_args* a, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_kernel<BN, A_MN, B_MN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::kSmemBytes);
+    if (e != cudaSuccess) {
+      fprintf(stderr, "bvc: cudaFuncSetAttribute(gemm) failed: %s\n", cudaGetErrorString(e));
+      return BVC_ERR_LAUNCH;
+    }
+    attr_done = true;
+  }
+  CUtensorMap ta, tb;
+  {
+    uint64_t dims[2], strides[1];
+    uint32_t box[2];
+    if (A_MN == 0) {
+      dims[0] = (uint64_t)a->K; dims[1] = (uint64_t)a->M; box[0] = BK; box[1] = BM;
+    } else {
+      dims[0] = (uint64_t)a->M; dims[1] = (uint64_t)a->K; box[0] = 64; box[1] = BK;
+    }
+    strides[0] = (uint64_t)a->lda * 2;
+    int rc = make_tmap(&ta, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a->a, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    if (B_MN == 0) {
+      dims[0] = (uint64_t)a->K; dims[1] = (uint64_t)a->N; box[0] = BK; box[1] = BN;
+    } else {
+      dims[0] = (uint64_t)a->N; dims[1] = (uint64_t)a->K; box[0] = 64; box[1] = BK;
+    }
+    strides[0] = (uint64_t)a->ldb * 2;
+    rc = make_tmap(&tb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a->b, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
+  CUtensorMap tp = ta;  // placeholder when unused
+  int has_pre = 0;
+  {
+    const void* base = nullptr;
+    uint64_t ld_bytes = 0;
+    CUtensorMapDataType dt = CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+    if (EPI == EPI_RES && a->res_idx == nullptr) { base = a->res; ld_bytes = (uint64_t)a->ldr * 4; }
+    if (EPI == EPI_LOSS) { base = a->target; ld_bytes = (uint64_t)a->ldt * 4; }
+    if (EPI == EPI_DGELU) { base = a->aux_in; ld_bytes = (uint64_t)a->ld_aux * 2; dt = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16; }
+    if (base != nullptr && (((uintptr_t)base) & 15) == 0 && ld_bytes % 16 == 0) {
+      const uint64_t dims[2] = {(uint64_t)a->N, (uint64_t)a->M};
+      const uint64_t strides[1] = {ld_bytes};
+      const uint32_t box[2] = {(uint32_t)BN, (uint32_t)BM};
+      if (make_tmap(&tp, dt, 2, base, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE) == BVC_OK) has_pre = 1;
+    }
+  }
+  GemmParams p;
+  p.has_pre = has_pre;
+  p.M = a->M; p.N = a->N; p.K = a->K;
+  p.tiles_m = (a->M + BM - 1) / BM;
+  p.tiles_n = (a->N + BN - 1) / BN;
+  p.kb_total = (a->K + BK - 1) / BK;
+  resolve_k_splits(a, BN, &p.kb_per_split, &p.k_splits);
+  p.out_f32 = a->out_f32; p.out_bf16 = (bf16*)a->out_bf16; p.ldo = a->ldo;
+  p.out_seg = a->out_seg; p.out_seg_stride = a->out_seg_stride; p.out_seg_off = a->out_seg_off;
+  p.alpha = a->alpha_host; p.alpha_dev = a->alpha_dev; p.bias = a->bias; p.act = a->act;
+  p.aux_out = (bf16*)a->aux_out; p.aux_in = (const bf16*)a->aux_in; p.ld_aux = a->ld_aux;
+  p.res = a->res; p.ldr = a->ldr; p.res_idx = a->res_idx;
+  p.target = a->target; p.ldt = a->ldt; p.loss_partial = a->loss_partial; p.logits_out = (bf16*)a->logits_out;
+  if (p.k_splits > 1) {
+    BVC_CHECK_ARG(a->out_f32 != nullptr && a->out_bf16 == nullptr && a->bias == nullptr && a->act == 0 &&
+                  a->res == nullptr && a->target == nullptr);
+  }
+  const long long total = (long long)p.tiles_m * p.tiles_n * p.k_splits;
+  const int sms = num_sms();
+  const int grid = (int)(total < sms ? total : sms);
+  gemm_kernel<BN, A_MN, B_MN, EPI><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, tp, p);
+  BVC_CHECK_LAUNCH();
+  return BVC_OK;
+}
+
+// every (operand-major, epilogue) combination the model uses gets its own lean kernel; anything else runs the
+// generic (all-runtime-flags) epilogue
+template <int BN>
+static int gemm_dispatch_bn(const bvc_gemm_args* a, int epi, cudaStream_t s) {
+  const int am = a->a_mn_major, bm = a->b_mn_major;
+  if (am == 0 && bm == 0) {
+    switch (epi) {
+      case EPI_PLAIN: return launch_gemm<BN, 0, 0, EPI_PLAIN>(a, s);
+      case EPI_GELU: return launch_gemm<BN, 0, 0, EPI_GELU>(a, s);
+      case EPI_RES: return launch_gemm<BN, 0, 0, EPI_RES>(a, s);
+      case EPI_LOSS: return launch_gemm<BN, 0, 0, EPI_LOSS>(a, s);
+      default: return launch_gemm<BN, 0, 0, EPI_GENERIC>(a, s);
+    }
+  }
+  if (am == 0 && bm == 1) {
+    switch (epi) {
+      case EPI_PLAIN: return launch_gemm<BN, 0, 1, EPI_PLAIN>(a, s);
+      case EPI_DGELU: return launch_gemm<BN, 0, 1, EPI_DGELU>(a, s);
+      default: return launch_gemm<BN, 0, 1, EPI_GENERIC>(a, s);
+    }
+  }
+  if (am == 1 && bm == 1) {
+    if (epi == EPI_SPLITK) return launch_gemm<BN, 1, 1, EPI_SPLITK>(a, s);
+    return launch_gemm<BN, 1, 1, EPI_GENERIC>(a, s);
+  }
+  return launch_gemm<BN, 1, 0, EPI_GENERIC>(a, s);
+}
+
+}  // namespace bvc

@@ -76,18 +76,20 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const bf16* __restri
                                                             const float* __restrict__ gamma,
                                                             const float* __restrict__ dres, int M, int d,
                                                             float* __restrict__ dx_f32, bf16* __restrict__ dx_bf16,
-                                                            float* __restrict__ dgamma, float* __restrict__ dbeta) {
+                                                            float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                            float* __restrict__ dxsum) {
   const int lane = threadIdx.x & 31;
   const int warps_per_block = blockDim.x >> 5;
   const int nvec = d >> 2;
   const float inv_d = 1.0f / (float)d;
-  float4 gam[VPL], dg[VPL], db[VPL];
+  float4 gam[VPL], dg[VPL], db[VPL], ds[VPL];
 #pragma unroll
   for (int i = 0; i < VPL; ++i) {
     const int c = lane + i * 32;
     gam[i] = (c < nvec) ? __ldg(reinterpret_cast<const float4*>(gamma) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
     dg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     db[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    ds[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   for (int r = blockIdx.x * warps_per_block + (threadIdx.x >> 5); r < M; r += gridDim.x * warps_per_block) {
     const long long pr = xs.row(r);
@@ -127,6 +129,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const bf16* __restri
           const float4 rv = __ldg(reinterpret_cast<const float4*>(dres + pr * ldx) + c);
           o.x += rv.x; o.y += rv.y; o.z += rv.z; o.w += rv.w;
         }
+        ds[i].x += o.x; ds[i].y += o.y; ds[i].z += o.z; ds[i].w += o.w;
         if (dx_f32) reinterpret_cast<float4*>(dx_f32 + pr * ldx)[c] = o;
         if (dx_bf16) {
           uint2 pk;
@@ -137,24 +140,26 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const bf16* __restri
       }
     }
   }
-  // block reduction of dgamma / dbeta through shared memory, then one atomic per column per block
-  extern __shared__ float sh[];  // [2][d]
-  for (int i = threadIdx.x; i < 2 * d; i += blockDim.x) sh[i] = 0.f;
-  __syncthreads();
+  // block reduction through shared memory ([warps][d] partials, fixed summation order), then one global atomic
+  // per column per block
+  extern __shared__ float sh[];
+  const int wid = threadIdx.x >> 5;
+#pragma unroll 1
+  for (int pass = 0; pass < 3; ++pass) {
+    float* dst = pass == 0 ? dgamma : (pass == 1 ? dbeta : dxsum);
+    if (dst == nullptr) continue;
 #pragma unroll
-  for (int i = 0; i < VPL; ++i) {
-    const int c = lane + i * 32;
-    if (c < nvec) {
-      atomicAdd(&sh[4 * c + 0], dg[i].x); atomicAdd(&sh[4 * c + 1], dg[i].y);
-      atomicAdd(&sh[4 * c + 2], dg[i].z); atomicAdd(&sh[4 * c + 3], dg[i].w);
-      atomicAdd(&sh[d + 4 * c + 0], db[i].x); atomicAdd(&sh[d + 4 * c + 1], db[i].y);
-      atomicAdd(&sh[d + 4 * c + 2], db[i].z); atomicAdd(&sh[d + 4 * c + 3], db[i].w);
+    for (int i = 0; i < VPL; ++i) {
+      const int c = lane + i * 32;
+      if (c < nvec) reinterpret_cast<float4*>(sh + wid * d)[c] = pass == 0 ? dg[i] : (pass == 1 ? db[i] : ds[i]);
     }
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < d; i += blockDim.x) {
-    atomicAdd(dgamma + i, sh[i]);
-    atomicAdd(dbeta + i, sh[d + i]);
+    __syncthreads();
+    for (int col = threadIdx.x; col < d; col += blockDim.x) {
+      float t = 0.f;
+      for (int k = 0; k < warps_per_block; ++k) t += sh[k * d + col];
+      atomicAdd(dst + col, t);
+    }
+    __syncthreads();
   }
 }
 
@@ -163,11 +168,11 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const bf16* __restri
 template <bool F32>
 __global__ void __launch_bounds__(256) colsum_kernel(const void* __restrict__ in, long long ld, Seg s, int M, int N,
                                                      float scale, const float* __restrict__ scale_dev,
-                                                     float* __restrict__ out) {
+                                                     float* __restrict__ out, int rows_per_block) {
   const int lane = threadIdx.x & 31, wy = threadIdx.x >> 5;
   const int c = blockIdx.x * 256 + lane * 8;
-  const int r0 = blockIdx.y * 256;
-  const int r1 = min(M, r0 + 256);
+  const int r0 = blockIdx.y * rows_per_block;
+  const int r1 = min(M, r0 + rows_per_block);
   float acc[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[j] = 0.f;
@@ -219,6 +224,38 @@ __global__ void __launch_bounds__(256) cast_kernel(const float* __restrict__ src
   if (blockIdx.x == 0 && threadIdx.x < (n & 7)) {
     const long long i = (nv << 3) + threadIdx.x;
     dst[i] = __float2bfloat16_rn(src[i]);
+  }
+}
+
+// one launch for every weight of the model: entry t copies (dst fp32) or casts (dst bf16) counts[t] fp32 elements
+struct CastEntry {
+  const float* src;
+  void* dst;
+  long long n;      // elements; src and dst 16-byte aligned
+  int dst_is_f32;
+  int pad;
+};
+__global__ void __launch_bounds__(256) cast_multi_kernel(const CastEntry* __restrict__ table) {
+  const CastEntry en = table[blockIdx.y];
+  const long long nv = en.n >> 3;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += stride) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(en.src) + 2 * i);
+    const float4 b = __ldg(reinterpret_cast<const float4*>(en.src) + 2 * i + 1);
+    if (en.dst_is_f32) {
+      reinterpret_cast<float4*>(en.dst)[2 * i] = a;
+      reinterpret_cast<float4*>(en.dst)[2 * i + 1] = b;
+    } else {
+      uint4 o;
+      o.x = pack_bf16x2(a.x, a.y); o.y = pack_bf16x2(a.z, a.w);
+      o.z = pack_bf16x2(b.x, b.y); o.w = pack_bf16x2(b.z, b.w);
+      reinterpret_cast<uint4*>(en.dst)[i] = o;
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (en.n & 7)) {
+    const long long i = (nv << 3) + threadIdx.x;
+    if (en.dst_is_f32) reinterpret_cast<float*>(en.dst)[i] = en.src[i];
+    else reinterpret_cast<bf16*>(en.dst)[i] = __float2bfloat16_rn(en.src[i]);
   }
 }
 
@@ -298,7 +335,7 @@ extern "C" int bvc_layernorm_fwd(const float* x, int64_t ldx, int32_t x_seg, int
 extern "C" int bvc_layernorm_bwd(const void* dy, const float* x, int64_t ldx, int32_t x_seg, int32_t x_seg_stride,
                                  int32_t x_seg_off, const float* mean, const float* rstd, const float* gamma,
                                  const float* dres, int32_t M, int32_t d, float* dx_f32, void* dx_bf16, float* dgamma,
-                                 float* dbeta, void* stream) {
+                                 float* dbeta, float* dxsum, void* stream) {
   BVC_CHECK_ARG(dy && x && mean && rstd && gamma && dgamma && dbeta && (dx_f32 || dx_bf16));
   BVC_CHECK_ARG(M > 0 && d > 0 && d % 4 == 0 && d <= 128 * kLnMaxVec && ldx % 4 == 0 && ldx >= d);
   Seg s{x_seg, x_seg_stride, x_seg_off};
@@ -306,10 +343,10 @@ extern "C" int bvc_layernorm_bwd(const void* dy, const float* x, int64_t ldx, in
   int grid = num_sms() * 2;
   if (grid > (M + 7) / 8) grid = (M + 7) / 8;
   cudaStream_t st = (cudaStream_t)stream;
-  const size_t shm = 2 * (size_t)d * sizeof(float);
+  const size_t shm = 8 * (size_t)d * sizeof(float);  // [warps][d], <= 32 KB
   BVC_LN_DISPATCH(vpl, (layernorm_bwd_kernel<V><<<grid, 256, shm, st>>>((const bf16*)dy, x, ldx, s, mean, rstd, gamma,
                                                                          dres, M, d, dx_f32, (bf16*)dx_bf16, dgamma,
-                                                                         dbeta)));
+                                                                         dbeta, dxsum)));
   BVC_CHECK_LAUNCH();
   return BVC_OK;
 }
@@ -319,12 +356,15 @@ extern "C" int bvc_colsum(const void* in, int32_t in_is_f32, int64_t ld, int32_t
                           void* stream) {
   BVC_CHECK_ARG(in && out && M > 0 && N > 0 && N % 8 == 0 && ld % 8 == 0);
   Seg s{seg, seg_stride, seg_off};
-  dim3 grid((N + 255) / 256, (M + 255) / 256);
+  const int gx = (N + 255) / 256;
+  int rpb = 256;  // shrink the row chunk until the grid covers the machine ~3x (small M would leave SMs idle)
+  while (rpb > 32 && (long long)gx * ((M + rpb - 1) / rpb) < 3LL * num_sms()) rpb >>= 1;
+  dim3 grid(gx, (M + rpb - 1) / rpb);
   cudaStream_t st = (cudaStream_t)stream;
   if (in_is_f32)
-    colsum_kernel<true><<<grid, 256, 0, st>>>(in, ld, s, M, N, scale_host, scale_dev, out);
+    colsum_kernel<true><<<grid, 256, 0, st>>>(in, ld, s, M, N, scale_host, scale_dev, out, rpb);
   else
-    colsum_kernel<false><<<grid, 256, 0, st>>>(in, ld, s, M, N, scale_host, scale_dev, out);
+    colsum_kernel<false><<<grid, 256, 0, st>>>(in, ld, s, M, N, scale_host, scale_dev, out, rpb);
   BVC_CHECK_LAUNCH();
   return BVC_OK;
 }
@@ -332,6 +372,14 @@ extern "C" int bvc_colsum(const void* in, int32_t in_is_f32, int64_t ld, int32_t
 extern "C" int bvc_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream) {
   BVC_CHECK_ARG(src && dst && n > 0 && (((uintptr_t)src) & 15) == 0 && (((uintptr_t)dst) & 15) == 0);
   cast_kernel<<<grid_for(n / 8 + 1, 256), 256, 0, (cudaStream_t)stream>>>(src, (bf16*)dst, (long long)n);
+  BVC_CHECK_LAUNCH();
+  return BVC_OK;
+}
+
+extern "C" int bvc_cast_multi(const void* table, int32_t n_entries, void* stream) {
+  BVC_CHECK_ARG(table && n_entries > 0 && n_entries <= 65535);
+  dim3 grid(32, n_entries);
+  cast_multi_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const CastEntry*)table);
   BVC_CHECK_LAUNCH();
   return BVC_OK;
 }

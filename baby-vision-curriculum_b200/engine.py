@@ -24,71 +24,107 @@ def _empty(shape, dtype, dev):
 
 
 class Bf16Cache:
-    """bf16 copies of the fp32 master weights (what autocast re-casts on every call, HF linear layers), refreshed
-    only when a parameter's storage or version counter changes (i.e. after an optimizer step / load_state_dict)."""
+    """bf16 copies of the fp32 master weights (what autocast re-casts on every call, HF linear layers) in ONE flat
+    buffer, refreshed by a single bvc_cast_multi launch whenever any parameter's storage or version counter changed
+    (i.e. after an optimizer step / load_state_dict).  Also packs (q_bias, 0, v_bias) into the fused QKV bias."""
 
     def __init__(self):
-        self._store = {}
+        self._plan = None       # (ptr signature, table tensor, n_entries, total elems, views)
+        self._versions = None
+        self._params = []
 
-    def _key(self, params):
-        return tuple((p.data_ptr(), p._version) for p in params)
-
-    def weight(self, name, p):
-        ent = self._store.get(name)
-        key = self._key((p,))
-        if ent is None or ent[0] != key or ent[1].device != p.device:
-            buf = ent[1] if ent is not None and ent[1].device == p.device and ent[1].numel() == p.numel() else \
-                _empty((p.numel(),), BF16, p.device)
-            L.cast_bf16(p.detach().reshape(-1), buf)
-            ent = (key, buf)
-            self._store[name] = ent
-        return ent[1]
-
-    def qkv(self, name, wq, wk, wv, qb, vb):
-        """packed [3d, d] bf16 weight and [3d] fp32 bias (q_bias, 0, v_bias) -- HF:239-242 as one GEMM."""
-        ent = self._store.get(name)
-        key = self._key((wq, wk, wv, qb, vb))
-        if ent is None or ent[0] != key or ent[1].device != wq.device:
-            d = wq.shape[0]
-            if ent is not None and ent[1].device == wq.device:
-                w, b = ent[1], ent[2]
+    def register(self, entries, device):
+        """entries: list of (name, kind, params) with kind 'w' (one weight) or 'qkv' (wq, wk, wv, qb, vb)."""
+        sig = tuple(p.data_ptr() for _, _, ps in entries for p in ps) + (str(device),)
+        if self._plan is not None and self._plan[0] == sig:
+            return
+        n_bf16 = 0
+        n_f32 = 0
+        for _, kind, ps in entries:
+            if kind == "w":
+                n_bf16 += (ps[0].numel() + 7) // 8 * 8
             else:
-                w = _empty((3 * d * d,), BF16, wq.device)
-                b = torch.zeros(3 * d, dtype=F32, device=wq.device)
-            for i, p in enumerate((wq, wk, wv)):
-                L.cast_bf16(p.detach().reshape(-1), w[i * d * d:(i + 1) * d * d])
-            b[0:d].copy_(qb.detach())
-            b[2 * d:3 * d].copy_(vb.detach())
-            ent = (key, w, b)
-            self._store[name] = ent
-        return ent[1], ent[2]
+                d = ps[0].shape[0]
+                n_bf16 += 3 * d * d
+                n_f32 += 3 * d
+        wbuf = torch.empty(n_bf16, dtype=BF16, device=device)
+        bbuf = torch.zeros(max(n_f32, 8), dtype=F32, device=device)
+        rows, views, ow, ob, total = [], {}, 0, 0, 0
+        self._params = []
+
+        def add(src, dst_ptr, n, is_f32):
+            nonlocal total
+            rows.append((src.data_ptr(), dst_ptr, n, 1 if is_f32 else 0))
+            total += n
+            self._params.append(src)
+
+        for name, kind, ps in entries:
+            if kind == "w":
+                n = ps[0].numel()
+                views[name] = wbuf[ow:ow + n]
+                add(ps[0], wbuf.data_ptr() + 2 * ow, n, False)
+                ow += (n + 7) // 8 * 8
+            else:
+                wq, wk, wv, qb, vb = ps
+                d = wq.shape[0]
+                views[name] = (wbuf[ow:ow + 3 * d * d], bbuf[ob:ob + 3 * d])
+                for i, w in enumerate((wq, wk, wv)):
+                    add(w, wbuf.data_ptr() + 2 * (ow + i * d * d), d * d, False)
+                add(qb, bbuf.data_ptr() + 4 * ob, d, True)
+                add(vb, bbuf.data_ptr() + 4 * (ob + 2 * d), d, True)
+                ow += 3 * d * d
+                ob += 3 * d
+        import numpy as np
+        tab = np.zeros((len(rows), 4), dtype=np.int64)
+        for i, (sp, dp, n, f) in enumerate(rows):
+            tab[i] = (sp, dp, n, f)  # {src, dst, n, dst_is_f32 | pad<<32} : 4 x 8 bytes
+        table = torch.from_numpy(tab).to(device)
+        self._plan = (sig, table, len(rows), total, views, wbuf, bbuf)
+        self._versions = None
+
+    def refresh(self):
+        ver = tuple(p._version for p in self._params)
+        if ver != self._versions:
+            _, table, n, total, _, _, _ = self._plan
+            L.cast_multi(table, n, total)
+            self._versions = ver
+
+    def weight(self, name):
+        return self._plan[4][name]
+
+    def qkv(self, name):
+        return self._plan[4][name]
 
     def clear(self):
-        self._store.clear()
+        self._plan, self._versions, self._params = None, None, []
 
 
 class GradSideChannel:
-    """The bf16 twin of the most recent fp32 activation gradient (written by the same LayerNorm-backward kernel),
-    handed to the upstream stage so it does not have to re-cast its incoming gradient."""
+    """Companions of the most recent fp32 activation gradient, written by the kernel that produced it: its bf16 twin
+    (the next GEMM's A operand) and, when available, its column sums (the bias gradient of the Linear that fed this
+    residual stream) -- so the upstream stage neither re-casts nor re-reads its incoming gradient."""
 
     def __init__(self):
         self.ptr = None
         self.t = None
+        self.colsum = None
 
-    def put(self, g_f32, g_bf16):
-        self.ptr, self.t = g_f32.data_ptr(), g_bf16
+    def put(self, g_f32, g_bf16, colsum=None):
+        self.ptr, self.t, self.colsum = g_f32.data_ptr(), g_bf16, colsum
 
     def drop(self):
-        self.ptr, self.t = None, None
+        self.ptr, self.t, self.colsum = None, None, None
 
     def take(self, g_f32, M, d):
+        """-> (bf16 twin, column sums or None)"""
         if self.ptr == g_f32.data_ptr() and self.t is not None and self.t.numel() == M * d:
-            t, self.t, self.ptr = self.t, None, None
-            return t
-        self.t, self.ptr = None, None
+            t, cs = self.t, self.colsum
+            self.drop()
+            return t, cs
+        self.drop()
         out = _empty((M, d), BF16, g_f32.device)
         L.rows_to_bf16(g_f32, M, d, out)
-        return out
+        return out, None
 
 
 class StepState:
@@ -114,7 +150,7 @@ class EmbedFn(torch.autograd.Function):
         D = w.shape[0]
         K = w.numel() // D
         M = patches.shape[0]
-        wb = st.cache.weight(name, w)
+        wb = st.cache.weight(name)
         x = _empty((M, D), F32, patches.device)
         L.gemm(patches, wb, M, D, K, out_f32=x, bias=b.detach(), res=pos, ldr=D, res_idx=st.vis_idx)
         ctx.st, ctx.patches, ctx.dims, ctx.wshape = st, patches, (M, D, K), w.shape
@@ -125,11 +161,14 @@ class EmbedFn(torch.autograd.Function):
         st, patches = ctx.st, ctx.patches
         M, D, K = ctx.dims
         dx = _contig_grad(dx)
-        dxb = st.side.take(dx, M, D)
+        dxb, cs = st.side.take(dx, M, D)
         flat = torch.zeros(D * K + D, dtype=F32, device=dx.device)
         dw, db = flat[:D * K].view(ctx.wshape), flat[D * K:]
         L.gemm(dxb, patches, D, K, M, a_mn=True, b_mn=True, lda=D, ldb=K, out_f32=dw, k_splits=0)
-        L.colsum(dxb, M, D, db)
+        if cs is not None:
+            db = cs
+        else:
+            L.colsum(dxb, M, D, db)
         return dw, db, None, None, None, None
 
 
@@ -144,8 +183,8 @@ class BlockFn(torch.autograd.Function):
         M, d = x.shape
         ff = w1.shape[0]
         cache = st.cache
-        wqkv, bqkv = cache.qkv(name + "qkv", wq, wk, wv, qb, vb)
-        wob, w1b, w2b = cache.weight(name + "wo", wo), cache.weight(name + "w1", w1), cache.weight(name + "w2", w2)
+        wqkv, bqkv = cache.qkv(name + "qkv")
+        wob, w1b, w2b = cache.weight(name + "wo"), cache.weight(name + "w1"), cache.weight(name + "w2")
         scale = float((d // H) ** -0.5)
 
         u1 = _empty((M, d), BF16, dev)
@@ -178,22 +217,26 @@ class BlockFn(torch.autograd.Function):
         ctx.saved = None
         dev = dxo.device
         dxo = _contig_grad(dxo)
-        dxob = st.side.take(dxo, M, d)
+        dxob, cs_out = st.side.take(dxo, M, d)
 
-        # every atomically-accumulated output of this block in one zero-filled buffer (one memset)
-        sizes = [d, d, 3 * d * d, 3 * d, d * d, d, d, d, ff * d, ff, d * ff, d]
+        # every atomically-accumulated output of this block in one zero-filled buffer (one memset); the last slot
+        # collects colsum(dx) of this block's input gradient for the stage upstream
+        sizes = [d, d, 3 * d * d, 3 * d, d * d, d, d, d, ff * d, ff, d * ff, d, d]
         flat = torch.zeros(sum(sizes), dtype=F32, device=dev)
         views, o = [], 0
         for s_ in sizes:
             views.append(flat[o:o + s_])
             o += s_
-        g_ln1w, g_ln1b, g_wqkv, g_bqkv, g_wo, g_bo, g_ln2w, g_ln2b, g_w1, g_b1, g_w2, g_b2 = views
+        g_ln1w, g_ln1b, g_wqkv, g_bqkv, g_wo, g_bo, g_ln2w, g_ln2b, g_w1, g_b1, g_w2, g_b2, cs_in = views
 
         # fc2: x_out = x_mid + act.W2^T + b2
         d_pre = _empty((M, ff), BF16, dev)
         L.gemm(dxob, w2b, M, ff, d, b_mn=True, ldb=ff, out_bf16=d_pre, act=2, aux_in=pre, ld_aux=ff)
         L.gemm(dxob, act, d, ff, M, a_mn=True, b_mn=True, lda=d, ldb=ff, out_f32=g_w2, k_splits=0)
-        L.colsum(dxob, M, d, g_b2)
+        if cs_out is not None:
+            g_b2 = cs_out
+        else:
+            L.colsum(dxob, M, d, g_b2)
         del act, pre
         # fc1: pre = u2.W1^T + b1
         L.gemm(d_pre, u2, ff, d, M, a_mn=True, b_mn=True, lda=ff, ldb=d, out_f32=g_w1, k_splits=0)
@@ -204,13 +247,13 @@ class BlockFn(torch.autograd.Function):
         # LN2 backward + residual branch
         dxm = _empty((M, d), F32, dev)
         dxmb = _empty((M, d), BF16, dev)
-        L.layernorm_bwd(d_u2, x_mid, stats[2], stats[3], ln2w.detach(), dxo, M, d, dxm, dxmb, g_ln2w, g_ln2b)
+        L.layernorm_bwd(d_u2, x_mid, stats[2], stats[3], ln2w.detach(), dxo, M, d, dxm, dxmb, g_ln2w, g_ln2b,
+                        dxsum=g_bo)  # colsum(dx_mid) is the out-proj bias gradient
         del d_u2, x_mid
         # attention output projection: x_mid = x + attn.Wo^T + bo
         d_attn = _empty((M, d), BF16, dev)
         L.gemm(dxmb, wob, M, d, d, b_mn=True, ldb=d, out_bf16=d_attn)
         L.gemm(dxmb, attn, d, d, M, a_mn=True, b_mn=True, lda=d, ldb=d, out_f32=g_wo, k_splits=0)
-        L.colsum(dxmb, M, d, g_bo)
         # attention core
         dqkv = _empty((M, 3 * d), BF16, dev)
         delta = _empty((B, H, S), F32, dev)
@@ -225,8 +268,8 @@ class BlockFn(torch.autograd.Function):
         # LN1 backward + residual
         dx = _empty((M, d), F32, dev)
         dxb = _empty((M, d), BF16, dev)
-        L.layernorm_bwd(d_u1, x, stats[0], stats[1], ln1w.detach(), dxm, M, d, dx, dxb, g_ln1w, g_ln1b)
-        st.side.put(dx, dxb)
+        L.layernorm_bwd(d_u1, x, stats[0], stats[1], ln1w.detach(), dxm, M, d, dx, dxb, g_ln1w, g_ln1b, dxsum=cs_in)
+        st.side.put(dx, dxb, cs_in)
 
         gw = g_wqkv.view(3, d, d)
         return (dx, g_ln1w, g_ln1b, gw[0], gw[1], gw[2], g_bqkv[0:d], g_bqkv[2 * d:3 * d], g_wo.view(d, d), g_bo,
@@ -243,7 +286,7 @@ class EncToDecFn(torch.autograd.Function):
         M, D = h.shape
         Dd = w.shape[0]
         B, N, nv = st.B, st.N, st.nv
-        wb = st.cache.weight(name, w)
+        wb = st.cache.weight(name)
         hb = _empty((M, D), BF16, dev)
         L.rows_to_bf16(h, M, D, hb)
         xf = _empty((B * N, Dd), F32, dev)
@@ -264,7 +307,7 @@ class EncToDecFn(torch.autograd.Function):
         dz = _empty((M, Dd), BF16, dev)
         L.rows_to_bf16(dxf, M, Dd, dz, ld=Dd, seg=(nv, N, 0))
         flat = torch.zeros(Dd * D + Dd, dtype=F32, device=dev)
-        g_w, g_tok = flat[:Dd * D].view(Dd, D), flat[Dd * D:]
+        g_w, g_tok = flat[:Dd * D].view(Dd, D), flat[Dd * D:Dd * D + Dd]
         dh = _empty((M, D), F32, dev)
         dhb = _empty((M, D), BF16, dev)
         L.gemm(dz, wb, M, D, Dd, b_mn=True, ldb=D, out_f32=dh, out_bf16=dhb)
@@ -287,7 +330,7 @@ class HeadLossFn(torch.autograd.Function):
         Dd = xf.shape[1]
         K = wh.shape[0]
         M = B * nm
-        whb = st.cache.weight(name, wh)
+        whb = st.cache.weight(name)
         z = _empty((M, Dd), BF16, dev)
         stats = _empty((2, M), F32, dev)
         L.layernorm_fwd(xf, nw.detach(), nb.detach(), 1e-5, M, Dd, z, stats[0], stats[1], ldx=Dd, seg=(nm, N, nv))
@@ -312,9 +355,10 @@ class HeadLossFn(torch.autograd.Function):
         dev = xf.device
         g = g.detach().to(F32).reshape(1).contiguous()
         alpha = 2.0 / (float(M) * K)
-        flat = torch.zeros(K * Dd + K + 2 * Dd, dtype=F32, device=dev)
+        flat = torch.zeros(K * Dd + K + 3 * Dd, dtype=F32, device=dev)
         g_wh, g_bh = flat[:K * Dd].view(K, Dd), flat[K * Dd:K * Dd + K]
-        g_nw, g_nb = flat[K * Dd + K:K * Dd + K + Dd], flat[K * Dd + K + Dd:]
+        o = K * Dd + K
+        g_nw, g_nb, cs = flat[o:o + Dd], flat[o + Dd:o + 2 * Dd], flat[o + 2 * Dd:]
         dz = _empty((M, Dd), BF16, dev)
         L.gemm(diff, whb, M, Dd, K, b_mn=True, ldb=Dd, out_bf16=dz, alpha=alpha, alpha_dev=g)
         L.gemm(diff, z, K, Dd, M, a_mn=True, b_mn=True, lda=K, ldb=Dd, out_f32=g_wh, k_splits=0, alpha=alpha,
@@ -323,6 +367,6 @@ class HeadLossFn(torch.autograd.Function):
         dxf = torch.zeros((B * N, Dd), dtype=F32, device=dev)      # visible rows get no gradient from the head
         dxfb = torch.zeros((B * N, Dd), dtype=BF16, device=dev)
         L.layernorm_bwd(dz, xf, stats[0], stats[1], nw.detach(), None, M, Dd, dxf, dxfb, g_nw, g_nb, ldx=Dd,
-                        seg=(nm, N, nv))
-        st.side.put(dxf, dxfb)
+                        seg=(nm, N, nv), dxsum=cs)  # visible rows are zero: colsum over the Nm rows == over all rows
+        st.side.put(dxf, dxfb, cs)
         return dxf, g_nw, g_nb, g_wh, g_bh, None, None, None, None

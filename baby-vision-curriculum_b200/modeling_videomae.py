@@ -220,6 +220,20 @@ class VideoMAEForPreTraining(nn.Module):
             self._pos_dev[dev] = t
         return t
 
+    def _weight_entries(self):
+        ents = [("pe", "w", (self.videomae.embeddings.patch_embeddings.projection.weight,))]
+        for tag, layers in (("e", self.videomae.encoder.layer), ("d", self.decoder.decoder_layers)):
+            for i, layer in enumerate(layers):
+                a = layer.attention.attention
+                n = f"{tag}{i}."
+                ents.append((n + "qkv", "qkv", (a.query.weight, a.key.weight, a.value.weight, a.q_bias, a.v_bias)))
+                ents.append((n + "wo", "w", (layer.attention.output.dense.weight,)))
+                ents.append((n + "w1", "w", (layer.intermediate.dense.weight,)))
+                ents.append((n + "w2", "w", (layer.output.dense.weight,)))
+        ents.append(("e2d", "w", (self.encoder_to_decoder.weight,)))
+        ents.append(("head", "w", (self.decoder.head.weight,)))
+        return ents
+
     def check_mask_status(self):
         """Synchronise and raise if any forward since the last check saw rows with unequal mask counts."""
         if self._status is not None and int(self._status.item()) != 0:
@@ -285,6 +299,8 @@ class VideoMAEForPreTraining(nn.Module):
 
             pos_e, pos_d = self._pos(dev)
             proj = self.videomae.embeddings.patch_embeddings.projection
+            self._cache.register(self._weight_entries(), dev)
+            self._cache.refresh()
             h = EmbedFn.apply(proj.weight, proj.bias, patches, pos_e, st, "pe")
             for i, layer in enumerate(self.videomae.encoder.layer):
                 h = BlockFn.apply(h, *layer.flat_params(), st, f"e{i}.", B, nv, c.num_attention_heads,

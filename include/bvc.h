@@ -28,7 +28,7 @@ extern "C" {
 #define BVC_ERR_ARG (-1)
 #define BVC_ERR_DRIVER (-2)
 #define BVC_ERR_LAUNCH (-3)
-#define BVC_ABI_VERSION 3
+#define BVC_ABI_VERSION 4
 
 /* library / build info: returns BVC_ABI_VERSION (bumped when a signature changes) */
 int bvc_abi_version(void);
@@ -123,7 +123,9 @@ int bvc_loss_finalize(const float* partials, int64_t n, double numel, const int3
  *   x fp32 [*, d] with segment remap (x_seg...) ; y bf16 [M, d] compact; mean/rstd fp32 [M].  d % 4 == 0, d <= 1024.
  * Backward: dx = rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * gamma  (+ dres if given);
  *   dx_f32 / dx_bf16 (either may be null) are written at the remapped rows, dres read at the remapped rows;
- *   dgamma/dbeta fp32 [d] are ACCUMULATED atomically (caller zero-fills).
+ *   dgamma/dbeta fp32 [d] are ACCUMULATED atomically (caller zero-fills); dxsum (optional) accumulates the column
+ *   sums of the produced dx the same way -- it IS the bias gradient of the Linear whose output this LayerNorm's
+ *   input stream received (fc2 / attention out-proj / patch embedding), saving a separate pass.
  * ------------------------------------------------------------------------------------------------------ */
 int bvc_layernorm_fwd(const float* x, int64_t ldx, int32_t x_seg, int32_t x_seg_stride, int32_t x_seg_off,
                       const float* gamma, const float* beta, float eps, int32_t M, int32_t d, void* y,
@@ -131,7 +133,7 @@ int bvc_layernorm_fwd(const float* x, int64_t ldx, int32_t x_seg, int32_t x_seg_
 int bvc_layernorm_bwd(const void* dy, const float* x, int64_t ldx, int32_t x_seg, int32_t x_seg_stride,
                       int32_t x_seg_off, const float* mean, const float* rstd, const float* gamma,
                       const float* dres, int32_t M, int32_t d, float* dx_f32, void* dx_bf16, float* dgamma,
-                      float* dbeta, void* stream);
+                      float* dbeta, float* dxsum, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------
  * Column sums (bias gradients; mask_token gradient HF:528/591): out[c] += scale * sum_r in[row(r), c].
@@ -143,6 +145,10 @@ int bvc_colsum(const void* in, int32_t in_is_f32, int64_t ld, int32_t seg, int32
 
 /* fp32 -> bf16 cast of n contiguous elements (per-step weight cast that autocast does per call, HF linear layers) */
 int bvc_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream);
+/* Every weight of the model in ONE launch: `table` is a device array of n_entries records
+ *   { const float* src; void* dst; int64_t n; int32_t dst_is_f32; int32_t pad; }   (32 bytes each)
+ * entry t casts (dst bf16) or copies (dst fp32, used to pack q_bias / v_bias into the fused QKV bias) n elements. */
+int bvc_cast_multi(const void* table, int32_t n_entries, void* stream);
 /* rows of an fp32 [*, d] buffer (segment remap) -> compact bf16 [M, d]  (d % 4 == 0) */
 int bvc_rows_to_bf16(const float* src, int64_t ld, int32_t seg, int32_t seg_stride, int32_t seg_off, int32_t M,
                      int32_t d, void* dst, void* stream);

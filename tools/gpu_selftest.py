@@ -178,13 +178,14 @@ def ln_case(M, d, seg=(0, 0, 0)):
     dxb = torch.zeros(rows_phys, d, device=dev, dtype=torch.bfloat16)
     dg = torch.zeros(d, device=dev)
     db = torch.zeros(d, device=dev)
-    L.layernorm_bwd(dy, x, mean, rstd, gamma, dres, M, d, dxf, dxb, dg, db, seg=seg)
+    dsum = torch.zeros(d, device=dev)
+    L.layernorm_bwd(dy, x, mean, rstd, gamma, dres, M, d, dxf, dxb, dg, db, seg=seg, dxsum=dsum)
     ref.backward(dy.double())
     want = xr.grad + dres[pr].double()
     e1, e2 = relerr(dxf[pr], want), relerr(dxb[pr].float(), want)
-    e3, e4 = relerr(dg, gd.grad), relerr(db, bd.grad)
-    report(f"ln_bwd M{M} d{d} seg{seg}", e1 < 1e-5 and e2 < 4e-3 and e3 < 1e-4 and e4 < 1e-4,
-           f"dx {e1:.2e} dxb {e2:.2e} dgamma {e3:.2e} dbeta {e4:.2e}")
+    e3, e4, e5 = relerr(dg, gd.grad), relerr(db, bd.grad), relerr(dsum, want.sum(0))
+    report(f"ln_bwd M{M} d{d} seg{seg}", e1 < 1e-5 and e2 < 4e-3 and e3 < 1e-4 and e4 < 1e-4 and e5 < 1e-4,
+           f"dx {e1:.2e} dxb {e2:.2e} dgamma {e3:.2e} dbeta {e4:.2e} dxsum {e5:.2e}")
 
 
 @guarded

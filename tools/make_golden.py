@@ -45,9 +45,13 @@ def hf_model(cfg: O.OracleConfig, params):
     return m.train()
 
 
-def run_hf(cfg, params, x, mask):
+def run_hf(cfg, params, x, mask, bf16=False):
     m = hf_model(cfg, params)
-    out = m(x, bool_masked_pos=mask)
+    if bf16:  # the reference's own mixed-precision path (pretrain_videomae.py:306-308), on CPU autocast
+        with torch.autocast("cpu", dtype=torch.bfloat16):
+            out = m(x, bool_masked_pos=mask)
+    else:
+        out = m(x, bool_masked_pos=mask)
     out.loss.backward()
     grads = {k: p.grad.detach().clone() for k, p in m.named_parameters()}
     return out.loss.detach(), out.logits.detach(), grads
@@ -106,8 +110,19 @@ def summarised_step(name, batch, fname):
         np.random.seed(0)
         mask = O.batch_tube_masks(batch, cfg.grid, 0.9)
         loss, logits, grads = run_hf(cfg, params, x, mask)
+        bloss, _, bgrads = run_hf(cfg, params, x, mask, bf16=True)
         flat = logits.flatten()
+        bf16_dev = {k: abs(float(bgrads[k].double().norm()) - float(g.double().norm())) / max(float(g.double().norm()), 1e-30)
+                    for k, g in grads.items()}
+        bg = float(torch.sqrt(sum(g.double().pow(2).sum() for g in bgrads.values())))
+        fg = float(torch.sqrt(sum(g.double().pow(2).sum() for g in grads.values())))
         out[tag] = {
+            # how far the reference's OWN bf16-autocast path is from its fp32 path on these inputs
+            "hf_bf16_loss_rel": abs(float(bloss) - float(loss)) / float(loss),
+            "hf_bf16_grad_norm_rel": bf16_dev,
+            "hf_bf16_grad_global_norm_rel": abs(bg - fg) / fg,
+            "hf_bf16_grad_global_rel_l2": float(torch.sqrt(sum((bgrads[k].double() - g.double()).pow(2).sum()
+                                                               for k, g in grads.items()))) / fg,
             "loss": float(loss),
             "mask_row0_first_visible": [int(i) for i in np.nonzero(~mask[0].numpy())[0][:8]],
             "logits_sample_stride": 100003,

@@ -120,7 +120,7 @@ extern "C" int bvc_gemm_bf16(const bvc_gemm_args* a, void* stream) {
       epi = bvc::EPI_GELU;
     else if (a->act == 2 && a->out_bf16 && !a->out_f32 && !a->res && !a->target && !seg && !a->bias)
       epi = bvc::EPI_DGELU;
-    else if (a->res && a->out_f32 && !a->out_bf16 && a->act == 0 && !a->target)
+    else if (a->res && !a->res_idx && a->out_f32 && !a->out_bf16 && a->act == 0 && !a->target && !seg)
       epi = bvc::EPI_RES;
     else if (a->act == 0 && !a->res && !a->target && !seg && a->out_bf16 && !a->out_f32)
       epi = bvc::EPI_PLAIN;

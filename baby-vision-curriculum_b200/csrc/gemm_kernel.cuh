@@ -216,7 +216,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     const bool kDgelu = G ? p.act == 2 : EPI == EPI_DGELU;
     const bool kRes = G ? p.res != nullptr : EPI == EPI_RES;
     const bool kLoss = G ? p.target != nullptr : EPI == EPI_LOSS;
-    const bool kSeg = G || EPI == EPI_RES;
+    const bool kSeg = G;
     const bool kOutF32 = G ? p.out_f32 != nullptr : EPI == EPI_RES;
     const bool kOutBf16 = G ? p.out_bf16 != nullptr : (EPI == EPI_PLAIN || EPI == EPI_GELU || EPI == EPI_DGELU ||
                                                          EPI == EPI_LOSS);
@@ -254,19 +254,48 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
           // row loop serialises one DRAM round trip per row: measured 5x slower on the residual / GELU' GEMMs)
           float4 pre_f[8];
           uint2 pre_h[8];
+          if (!G && (kRes || kLoss || kDgelu)) {
+            // straight-line: clamp the row instead of predicating so the 8 loads issue back to back (the ncu source
+            // view of the predicated version showed one full memory round trip per row)
+            const float* fbase = kRes ? p.res : p.target;
+            const long long fld = kRes ? p.ldr : p.ldt;
 #pragma unroll
-          for (int it = 0; it < 8; ++it) {
-            const int r = rbase + it * 4 + rsub;
-            pre_f[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-            pre_h[it] = make_uint2(0u, 0u);
-            if (r < p.M) {
-              if (kRes) {
-                const long long rr = p.res_idx ? (long long)__ldg(p.res_idx + r) : (long long)r;
-                pre_f[it] = __ldg(reinterpret_cast<const float4*>(p.res + rr * p.ldr + col));
-              } else if (kLoss) {
-                pre_f[it] = __ldg(reinterpret_cast<const float4*>(p.target + (long long)r * p.ldt + col));
+            for (int it = 0; it < 8; ++it) {
+              const int rc = min(rbase + it * 4 + rsub, p.M - 1);
+              // volatile + memory clobber: ptxas otherwise sinks every load next to its use (one round trip per row)
+              if (kRes || kLoss)
+                asm volatile("ld.volatile.global.v4.f32 {%0, %1, %2, %3}, [%4];"
+                             : "=f"(pre_f[it].x), "=f"(pre_f[it].y), "=f"(pre_f[it].z), "=f"(pre_f[it].w)
+                             : "l"(fbase + (long long)rc * fld + col)
+                             : "memory");
+              if (kDgelu)
+                asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];"
+                             : "=r"(pre_h[it].x), "=r"(pre_h[it].y)
+                             : "l"(p.aux_in + (long long)rc * p.ld_aux + col)
+                             : "memory");
+            }
+            // one fake use of every loaded register: all 8 loads must have been issued before this point
+            if (kRes || kLoss)
+              asm volatile("" ::"f"(pre_f[0].x), "f"(pre_f[1].x), "f"(pre_f[2].x), "f"(pre_f[3].x), "f"(pre_f[4].x),
+                           "f"(pre_f[5].x), "f"(pre_f[6].x), "f"(pre_f[7].x));
+            if (kDgelu)
+              asm volatile("" ::"r"(pre_h[0].x), "r"(pre_h[1].x), "r"(pre_h[2].x), "r"(pre_h[3].x), "r"(pre_h[4].x),
+                           "r"(pre_h[5].x), "r"(pre_h[6].x), "r"(pre_h[7].x));
+          } else if (G) {
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              const int r = rbase + it * 4 + rsub;
+              pre_f[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+              pre_h[it] = make_uint2(0u, 0u);
+              if (r < p.M) {
+                if (kRes) {
+                  const long long rr = p.res_idx ? (long long)__ldg(p.res_idx + r) : (long long)r;
+                  pre_f[it] = __ldg(reinterpret_cast<const float4*>(p.res + rr * p.ldr + col));
+                } else if (kLoss) {
+                  pre_f[it] = __ldg(reinterpret_cast<const float4*>(p.target + (long long)r * p.ldt + col));
+                }
+                if (kDgelu) pre_h[it] = __ldg(reinterpret_cast<const uint2*>(p.aux_in + (long long)r * p.ld_aux + col));
               }
-              if (kDgelu) pre_h[it] = __ldg(reinterpret_cast<const uint2*>(p.aux_in + (long long)r * p.ld_aux + col));
             }
           }
 #pragma unroll

@@ -44,6 +44,37 @@ __device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+// packed fp32x2 arithmetic (sm_100 FFMA2 / FADD2 / FMUL2): halves the issue slots of the softmax-side math, which is
+// what bounds these kernels at head_dim 64 (ncu: issue-active 43 %, tensor pipe 25 %)
+__device__ __forceinline__ uint64_t pack2(float a, float b) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& a, float& b) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t fmul2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+
 // K-major operand tile [rows][64]: k-step (16 elements) = +32 bytes inside the swizzle atom
 __device__ __forceinline__ uint64_t desc_k(uint32_t base, int kstep) { return umma_smem_desc(base + kstep * 32, 1024, 16); }
 // MN-major operand tile [k rows][64 mn]: k-step (16 rows) = +2048 bytes; lbo = distance between 64-wide mn blocks
@@ -70,13 +101,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o
   uint8_t* sP = smem + 5 * kTileBytes;      // 32 KB
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 7 * kTileBytes);
   uint64_t* q_full = bars + 0;
-  uint64_t* kv_full = bars + 1;   // [2]
-  uint64_t* kv_empty = bars + 3;  // [2]
-  uint64_t* s_full = bars + 5;
-  uint64_t* s_free = bars + 6;
-  uint64_t* p_full = bars + 7;
-  uint64_t* o_full = bars + 8;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+  uint64_t* k_full = bars + 1;    // [2]   K and V have separate rings: a K stage is released as soon as its
+  uint64_t* k_empty = bars + 3;   // [2]   S = Q K^T MMA has run (long before the P V MMA of the same tile), which
+  uint64_t* v_full = bars + 5;    // [2]   gives the next K tile's TMA two softmax periods of lead time
+  uint64_t* v_empty = bars + 7;   // [2]
+  uint64_t* s_full = bars + 9;
+  uint64_t* s_free = bars + 10;
+  uint64_t* p_full = bars + 11;
+  uint64_t* o_full = bars + 12;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * kTile, h = blockIdx.y, b = blockIdx.z;
@@ -87,8 +120,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o
     tma_prefetch_desc(&tm_qkv);
     mbar_init(q_full, 1);
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&kv_full[i], 1);
-      mbar_init(&kv_empty[i], 1);
+      mbar_init(&k_full[i], 1);
+      mbar_init(&k_empty[i], 1);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&v_empty[i], 1);
     }
     mbar_init(s_full, 1);
     mbar_init(s_free, 4);
@@ -109,10 +144,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o
       tma_load_4d(sQ, &tm_qkv, q_full, 0, h, q0, b);
       for (int j = 0; j < n_kv; ++j) {
         const int st = j & 1;
-        mbar_wait(&kv_empty[st], ((uint32_t)(j >> 1) & 1u) ^ 1u);
-        mbar_expect_tx(&kv_full[st], 2 * kTileBytes);
-        tma_load_4d(sK + st * kTileBytes, &tm_qkv, &kv_full[st], 0, H + h, j * kTile, b);
-        tma_load_4d(sV + st * kTileBytes, &tm_qkv, &kv_full[st], 0, 2 * H + h, j * kTile, b);
+        const uint32_t par = ((uint32_t)(j >> 1) & 1u) ^ 1u;
+        mbar_wait(&k_empty[st], par);
+        mbar_expect_tx(&k_full[st], kTileBytes);
+        tma_load_4d(sK + st * kTileBytes, &tm_qkv, &k_full[st], 0, H + h, j * kTile, b);
+        mbar_wait(&v_empty[st], par);
+        mbar_expect_tx(&v_full[st], kTileBytes);
+        tma_load_4d(sV + st * kTileBytes, &tm_qkv, &v_full[st], 0, 2 * H + h, j * kTile, b);
       }
     }
   } else if (warp == 1) {
@@ -121,22 +159,25 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o
       constexpr uint32_t idesc_o = umma_idesc_bf16(64, 0, 1, 128);
       const uint32_t aQ = smem_u32(sQ), aP = smem_u32(sP);
       mbar_wait(q_full, 0);
-      mbar_wait(&kv_full[0], 0);
+      mbar_wait(&k_full[0], 0);
       tc_fence_after();
 #pragma unroll
       for (int k = 0; k < 4; ++k) umma_bf16_ss(tS, desc_k(aQ, k), desc_k(smem_u32(sK), k), idesc_s, k > 0);
       umma_commit(s_full);
+      umma_commit(&k_empty[0]);
       for (int j = 0; j < n_kv; ++j) {
         if (j + 1 < n_kv) {
           const int st = (j + 1) & 1;
-          mbar_wait(&kv_full[st], (uint32_t)((j + 1) >> 1) & 1u);
+          mbar_wait(&k_full[st], (uint32_t)((j + 1) >> 1) & 1u);
           mbar_wait(s_free, (uint32_t)j & 1u);
           tc_fence_after();
           const uint32_t aK = smem_u32(sK + st * kTileBytes);
 #pragma unroll
           for (int k = 0; k < 4; ++k) umma_bf16_ss(tS, desc_k(aQ, k), desc_k(aK, k), idesc_s, k > 0);
           umma_commit(s_full);
+          umma_commit(&k_empty[st]);
         }
+        mbar_wait(&v_full[j & 1], (uint32_t)(j >> 1) & 1u);
         mbar_wait(p_full, (uint32_t)j & 1u);
         tc_fence_after();
         const uint32_t aV = smem_u32(sV + (j & 1) * kTileBytes);
@@ -144,7 +185,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o
         for (int k = 0; k < 8; ++k)
           umma_bf16_ss(tO, desc_k(aP + (k >> 2) * kTileBytes, k & 3), desc_mn(aV, k, 8192), idesc_o, (j > 0 || k > 0));
         umma_commit(o_full);
-        umma_commit(&kv_empty[j & 1]);
+        umma_commit(&v_empty[j & 1]);
       }
     }
   } else {
@@ -155,24 +196,30 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o
     for (int j = 0; j < n_kv; ++j) {
       mbar_wait(s_full, (uint32_t)j & 1u);
       tc_fence_after();
-      uint32_t sv[4][32];
-#pragma unroll
-      for (int c = 0; c < 4; ++c) tmem_ld_32x32b_x32(tS + lane_base + c * 32, sv[c]);
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(s_free);
       const int valid = S - j * kTile;  // columns >= valid are past the end of the sequence
+      // pass 1: row maximum of the raw scores, two 32-column chunks of S in registers at a time (keeping all 128
+      // scores live spilled ~340 B per thread at the 168-register cap that 2 CTAs/SM imposes)
       float mx = -INFINITY;
 #pragma unroll
-      for (int c = 0; c < 4; ++c)
+      for (int hh = 0; hh < 2; ++hh) {
+        uint32_t sv[2][32];
+        tmem_ld_32x32b_x32(tS + lane_base + hh * 64, sv[0]);
+        tmem_ld_32x32b_x32(tS + lane_base + hh * 64 + 32, sv[1]);
+        tmem_ld_wait();
+        if (valid >= kTile) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float x = __uint_as_float(sv[c][i]) * scale_log2;
-          if (c * 32 + i >= valid) x = -INFINITY;
-          sv[c][i] = __float_as_uint(x);
-          mx = fmaxf(mx, x);
+          for (int c = 0; c < 2; ++c)
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) mx = fmax3(mx, __uint_as_float(sv[c][i]), __uint_as_float(sv[c][i + 1]));
+        } else {
+#pragma unroll
+          for (int c = 0; c < 2; ++c)
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (hh * 64 + c * 32 + i < valid) mx = fmaxf(mx, __uint_as_float(sv[c][i]));
         }
+      }
+      mx *= scale_log2;  // raw scores -> log2 domain (scale_log2 > 0)
       const bool need = mx > m_used + 8.0f;
       float alpha = 1.0f;
       if (need) {
@@ -196,22 +243,49 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o
         }
       }
       l *= alpha;
-      float lsum = 0.f;
+      // pass 2: P = exp2(S * scale_log2 - m), row sum, bf16 P into the swizzled A-operand tile
+      const uint64_t c2 = pack2(scale_log2, scale_log2), m2 = pack2(-m_used, -m_used);
+      uint64_t lsum2 = pack2(0.f, 0.f);
 #pragma unroll
-      for (int c = 0; c < 4; ++c)
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          float p[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            p[i] = exp2f(__uint_as_float(sv[c][g * 8 + i]) - m_used);
-            lsum += p[i];
-          }
-          uint4 pk;
-          pk.x = pack_bf16x2(p[0], p[1]); pk.y = pack_bf16x2(p[2], p[3]);
-          pk.z = pack_bf16x2(p[4], p[5]); pk.w = pack_bf16x2(p[6], p[7]);
-          *reinterpret_cast<uint4*>(sP + ptile_chunk_off(row, c * 4 + g)) = pk;
+      for (int hh = 0; hh < 2; ++hh) {
+        uint32_t sv[2][32];
+        tmem_ld_32x32b_x32(tS + lane_base + hh * 64, sv[0]);
+        tmem_ld_32x32b_x32(tS + lane_base + hh * 64 + 32, sv[1]);
+        tmem_ld_wait();
+        if (hh == 1) {  // S fully consumed: the MMA warp may overwrite it with the next tile's scores
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(s_free);
         }
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            float p[8];
+#pragma unroll
+            for (int i = 0; i < 8; i += 2) {
+              const int jj = g * 8 + i;
+              const uint64_t x2 = ffma2(pack2(__uint_as_float(sv[c][jj]), __uint_as_float(sv[c][jj + 1])), c2, m2);
+              float a, b;
+              unpack2(x2, a, b);
+              p[i] = exp2f(a);
+              p[i + 1] = exp2f(b);
+              if (valid < kTile) {  // warp-uniform: last K/V tile only
+                const int col = hh * 64 + c * 32 + jj;
+                if (col >= valid) p[i] = 0.f;
+                if (col + 1 >= valid) p[i + 1] = 0.f;
+              }
+              lsum2 = fadd2(lsum2, pack2(p[i], p[i + 1]));
+            }
+            uint4 pk;
+            pk.x = pack_bf16x2(p[0], p[1]); pk.y = pack_bf16x2(p[2], p[3]);
+            pk.z = pack_bf16x2(p[4], p[5]); pk.w = pack_bf16x2(p[6], p[7]);
+            *reinterpret_cast<uint4*>(sP + ptile_chunk_off(row, hh * 8 + c * 4 + g)) = pk;
+          }
+      }
+      float lsum, lsum_hi;
+      unpack2(lsum2, lsum, lsum_hi);
+      lsum += lsum_hi;
       l += lsum;
       fence_async_smem();
       tc_fence_before();
@@ -274,8 +348,10 @@ __global__ void __launch_bounds__(256) attn_delta_kernel(const bf16* __restrict_
 }
 
 constexpr int kBwdThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2-9 compute
-// resident pair (2 tiles) + stream ring (2 stages x 2 tiles) + P (32 KB) + dS (32 KB) + barriers
-constexpr int kBwdSmem = kTileBytes * (2 + 4) + 4 * kTileBytes + 128;
+// resident pair (2 tiles) + stream ring (4 stages x 2 tiles: the streamed tiles' TMA latency was the critical path
+// with 2 stages -- ncu: 30 % of the compute warps' samples waiting for S/dP) + P (32 KB) + dS (32 KB) + barriers
+constexpr int kBwdStages = 4;
+constexpr int kBwdSmem = kTileBytes * (2 + 2 * kBwdStages) + 4 * kTileBytes + 256;
 
 template <int MODE_KV>
 __global__ void __launch_bounds__(kBwdThreads, 1)
@@ -285,19 +361,19 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sR0 = smem;                     // MODE_KV: K_j    | MODE_Q: Q_i
   uint8_t* sR1 = smem + kTileBytes;        // MODE_KV: V_j    | MODE_Q: dO_i
-  uint8_t* sX = smem + 2 * kTileBytes;     // [2] MODE_KV: Q_i  | MODE_Q: K_j
-  uint8_t* sY = smem + 4 * kTileBytes;     // [2] MODE_KV: dO_i | MODE_Q: V_j
-  uint8_t* sP = smem + 6 * kTileBytes;     // 32 KB (MODE_KV only)
-  uint8_t* sD = smem + 8 * kTileBytes;     // 32 KB dS
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 10 * kTileBytes);
+  uint8_t* sX = smem + 2 * kTileBytes;                     // [stages] MODE_KV: Q_i  | MODE_Q: K_j
+  uint8_t* sY = smem + (2 + kBwdStages) * kTileBytes;      // [stages] MODE_KV: dO_i | MODE_Q: V_j
+  uint8_t* sP = smem + (2 + 2 * kBwdStages) * kTileBytes;  // 32 KB (MODE_KV only)
+  uint8_t* sD = sP + 2 * kTileBytes;                       // 32 KB dS
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sD + 2 * kTileBytes);
   uint64_t* r_full = bars + 0;
-  uint64_t* st_full = bars + 1;   // [2]
-  uint64_t* st_empty = bars + 3;  // [2]
-  uint64_t* sdp_full = bars + 5;
-  uint64_t* sdp_free = bars + 6;
-  uint64_t* pds_full = bars + 7;
-  uint64_t* pds_free = bars + 8;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+  uint64_t* st_full = bars + 1;                  // [stages]
+  uint64_t* st_empty = bars + 1 + kBwdStages;    // [stages]
+  uint64_t* sdp_full = bars + 1 + 2 * kBwdStages;
+  uint64_t* sdp_free = sdp_full + 1;
+  uint64_t* pds_full = sdp_full + 2;
+  uint64_t* pds_free = sdp_full + 3;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sdp_full + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int own0 = blockIdx.x * kTile, h = blockIdx.y, b = blockIdx.z;
@@ -308,7 +384,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
     tma_prefetch_desc(&tm_qkv);
     tma_prefetch_desc(&tm_do);
     mbar_init(r_full, 1);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < kBwdStages; ++i) {
       mbar_init(&st_full[i], 1);
       mbar_init(&st_empty[i], 1);
     }
@@ -336,8 +412,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
         tma_load_4d(sR1, &tm_do, r_full, 0, h, own0, b);
       }
       for (int i = 0; i < n_it; ++i) {
-        const int st = i & 1;
-        mbar_wait(&st_empty[st], ((uint32_t)(i >> 1) & 1u) ^ 1u);
+        const int st = i % kBwdStages;
+        mbar_wait(&st_empty[st], ((uint32_t)(i / kBwdStages) & 1u) ^ 1u);
         mbar_expect_tx(&st_full[st], 2 * kTileBytes);
         if (MODE_KV) {
           tma_load_4d(sX + st * kTileBytes, &tm_qkv, &st_full[st], 0, h, i * kTile, b);
@@ -353,7 +429,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
       constexpr uint32_t idesc_s = umma_idesc_bf16(128, 0, 0, 128);
       constexpr uint32_t idesc_tt = umma_idesc_bf16(64, 1, 1, 128);  // A MN-major, B MN-major (dV, dK)
       constexpr uint32_t idesc_q = umma_idesc_bf16(64, 0, 1, 128);   // A K-major, B MN-major (dQ)
-      const uint32_t aR0 = smem_u32(sR0), aR1 = smem_u32(sR1), aP = smem_u32(sP), aD = smem_u32(sD);
+      const uint32_t aR0 = smem_u32(sR0), aR1 = smem_u32(sR1);
       auto issue_s_dp = [&](int st) {
         const uint32_t aX = smem_u32(sX + st * kTileBytes), aY = smem_u32(sY + st * kTileBytes);
         // S = Q K^T, dP = dO V^T  (rows = q, cols = kv)
@@ -371,8 +447,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
       umma_commit(sdp_full);
       for (int i = 0; i < n_it; ++i) {
         if (i + 1 < n_it) {
-          const int st = (i + 1) & 1;
-          mbar_wait(&st_full[st], (uint32_t)((i + 1) >> 1) & 1u);
+          const int st = (i + 1) % kBwdStages;
+          mbar_wait(&st_full[st], (uint32_t)((i + 1) / kBwdStages) & 1u);
           mbar_wait(sdp_free, (uint32_t)i & 1u);
           tc_fence_after();
           issue_s_dp(st);
@@ -380,7 +456,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
         }
         mbar_wait(pds_full, (uint32_t)i & 1u);
         tc_fence_after();
-        const uint32_t aX = smem_u32(sX + (i & 1) * kTileBytes), aY = smem_u32(sY + (i & 1) * kTileBytes);
+        const int cst = i % kBwdStages;
+        const uint32_t aX = smem_u32(sX + cst * kTileBytes), aY = smem_u32(sY + cst * kTileBytes);
+        const uint32_t aP = smem_u32(sP), aD = smem_u32(sD);
         if (MODE_KV) {
           // dV[kv, d] += P^T dO : A = P (MN-major: m = kv, k = q), B = dO_i (MN-major: n = d, k = q)
 #pragma unroll
@@ -398,7 +476,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
                          (i > 0 || k > 0));
         }
         umma_commit(pds_free);
-        umma_commit(&st_empty[i & 1]);
+        umma_commit(&st_empty[cst]);
       }
     }
   } else {
@@ -408,28 +486,24 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
     const int row = q * 32 + lane;  // S / dP row = query index within the tile
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     const float c_log2 = scale * kLog2e;
-    float lse2 = 0.f, dl = 0.f;
-    if (!MODE_KV) {
-      const int qg = own0 + row;
-      if (qg < S) {
-        lse2 = __ldg(lse + ((long long)b * H + h) * S + qg) * kLog2e;
-        dl = __ldg(delta + ((long long)b * H + h) * S + qg);
+    const float* lse_bh = lse + ((long long)b * H + h) * S;
+    const float* dl_bh = delta + ((long long)b * H + h) * S;
+    // row statistics of query row `qg`: lse in the log2 domain and delta pre-multiplied by the softmax scale
+    // row statistics of query row `qg` (raw: the scaling happens at use, so a prefetch never stalls on its own load)
+    auto load_stats = [&](int qg, float& l_raw, float& d_raw) {
+      const int qc = min(qg, S - 1);
+      l_raw = __ldg(lse_bh + qc);
+      d_raw = __ldg(dl_bh + qc);
+      if (qg >= S) {
+        l_raw = 0.f;
+        d_raw = 0.f;
       }
-    }
+    };
+    float lse_r, dl_r, lse_n = 0.f, dl_n = 0.f;
+    load_stats(MODE_KV ? row : own0 + row, lse_r, dl_r);
+    const uint64_t cl2 = pack2(c_log2, c_log2), sc2 = pack2(scale, scale);
     for (int i = 0; i < n_it; ++i) {
-      int kv_valid;
-      if (MODE_KV) {
-        const int qg = i * kTile + row;
-        lse2 = 0.f;
-        dl = 0.f;
-        if (qg < S) {
-          lse2 = __ldg(lse + ((long long)b * H + h) * S + qg) * kLog2e;
-          dl = __ldg(delta + ((long long)b * H + h) * S + qg);
-        }
-        kv_valid = S - own0;
-      } else {
-        kv_valid = S - i * kTile;
-      }
+      const int kv_valid = MODE_KV ? S - own0 : S - i * kTile;
       mbar_wait(sdp_full, (uint32_t)i & 1u);
       tc_fence_after();
       uint32_t sv[2][32], dv[2][32];
@@ -437,40 +511,59 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
       for (int c = 0; c < 2; ++c) tmem_ld_32x32b_x32(tS + lane_base + half * 64 + c * 32, sv[c]);
 #pragma unroll
       for (int c = 0; c < 2; ++c) tmem_ld_32x32b_x32(tDP + lane_base + half * 64 + c * 32, dv[c]);
+      if (MODE_KV && i + 1 < n_it) load_stats((i + 1) * kTile + row, lse_n, dl_n);  // in flight during this tile
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(sdp_free);
       if (i > 0) mbar_wait(pds_free, (uint32_t)(i - 1) & 1u);  // previous dV/dK/dQ MMAs finished reading P / dS
+      uint8_t* bP = sP;
+      uint8_t* bD = sD;
+      const float lse2 = lse_r * kLog2e, dls = dl_r * scale;
+      const uint64_t nl2 = pack2(-lse2, -lse2), nd2 = pack2(-dls, -dls);
+      const bool tail = kv_valid < kTile;
 #pragma unroll
       for (int c = 0; c < 2; ++c)
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           float p[8], ds[8];
 #pragma unroll
-          for (int t = 0; t < 8; ++t) {
-            const int col = half * 64 + c * 32 + g * 8 + t;
-            float pv = exp2f(__uint_as_float(sv[c][g * 8 + t]) * c_log2 - lse2);
-            if (col >= kv_valid) pv = 0.f;
-            p[t] = pv;
-            ds[t] = pv * (__uint_as_float(dv[c][g * 8 + t]) - dl) * scale;
+          for (int t = 0; t < 8; t += 2) {
+            const int j = g * 8 + t;
+            const uint64_t x2 = ffma2(pack2(__uint_as_float(sv[c][j]), __uint_as_float(sv[c][j + 1])), cl2, nl2);
+            float a0, a1;
+            unpack2(x2, a0, a1);
+            p[t] = exp2f(a0);
+            p[t + 1] = exp2f(a1);
+            if (tail) {  // warp-uniform: only the last K/V tile of the sequence has columns past the end
+              const int col = half * 64 + c * 32 + j;
+              if (col >= kv_valid) p[t] = 0.f;
+              if (col + 1 >= kv_valid) p[t + 1] = 0.f;
+            }
+            // dS = P * (dP - delta) * scale
+            const uint64_t y2 = ffma2(pack2(__uint_as_float(dv[c][j]), __uint_as_float(dv[c][j + 1])), sc2, nd2);
+            unpack2(fmul2(pack2(p[t], p[t + 1]), y2), ds[t], ds[t + 1]);
           }
           const uint32_t off = ptile_chunk_off(row, half * 8 + c * 4 + g);
           if (MODE_KV) {
             uint4 pk;
             pk.x = pack_bf16x2(p[0], p[1]); pk.y = pack_bf16x2(p[2], p[3]);
             pk.z = pack_bf16x2(p[4], p[5]); pk.w = pack_bf16x2(p[6], p[7]);
-            *reinterpret_cast<uint4*>(sP + off) = pk;
+            *reinterpret_cast<uint4*>(bP + off) = pk;
           }
           uint4 dk;
           dk.x = pack_bf16x2(ds[0], ds[1]); dk.y = pack_bf16x2(ds[2], ds[3]);
           dk.z = pack_bf16x2(ds[4], ds[5]); dk.w = pack_bf16x2(ds[6], ds[7]);
-          *reinterpret_cast<uint4*>(sD + off) = dk;
+          *reinterpret_cast<uint4*>(bD + off) = dk;
         }
       fence_async_smem();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(pds_full);
+      if (MODE_KV) {
+        lse_r = lse_n;
+        dl_r = dl_n;
+      }
     }
     // epilogue: the accumulators (rows = owned tile rows, 64 cols); this warp writes 32 of the 64 columns
     mbar_wait(pds_free, (uint32_t)(n_it - 1) & 1u);

@@ -31,6 +31,25 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
+// Volatile vector loads.  ptxas sinks ordinary (and .nc) loads next to their first use to save registers, which turns a
+// batch of independent loads into one memory round trip per load (seen in the ncu source view of the GEMM epilogue and
+// of LayerNorm backward).  Volatile loads keep program order, so a loop of them really is N requests in flight.
+__device__ __forceinline__ float4 ldv_f4(const void* p) {
+  float4 v;
+  asm volatile("ld.volatile.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint2 ldv_u2(const void* p) {
+  uint2 v;
+  asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint4 ldv_u4(const void* p) {
+  uint4 v;
+  asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
+}
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&t);

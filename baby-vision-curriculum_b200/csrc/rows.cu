@@ -82,11 +82,9 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const bf16* __restri
   const int warps_per_block = blockDim.x >> 5;
   const int nvec = d >> 2;
   const float inv_d = 1.0f / (float)d;
-  float4 gam[VPL], dg[VPL], db[VPL], ds[VPL];
+  float4 dg[VPL], db[VPL], ds[VPL];
 #pragma unroll
   for (int i = 0; i < VPL; ++i) {
-    const int c = lane + i * 32;
-    gam[i] = (c < nvec) ? __ldg(reinterpret_cast<const float4*>(gamma) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
     dg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     db[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     ds[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -95,19 +93,30 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const bf16* __restri
     const long long pr = xs.row(r);
     const float4* xr = reinterpret_cast<const float4*>(x + pr * ldx);
     const uint2* dyr = reinterpret_cast<const uint2*>(dy + (long long)r * d);
+    const float4* rr = reinterpret_cast<const float4*>(dres + pr * ldx);
+    // every operand of the row first (3 x VPL independent 16-byte requests per lane in flight), then the math
+    float4 xh[VPL], g[VPL], rv[VPL];
+    uint2 dvv[VPL];
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int c = min(lane + i * 32, nvec - 1);
+      xh[i] = ldv_f4(xr + c);
+      dvv[i] = ldv_u2(dyr + c);
+      if (dres) rv[i] = ldv_f4(rr + c);
+    }
     const float mu = __ldg(mean + r), rs = __ldg(rstd + r);
-    float4 xh[VPL], g[VPL];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
       const int c = lane + i * 32;
       if (c < nvec) {
-        const float4 xv = __ldg(xr + c);
-        const uint2 dv = __ldg(dyr + c);
+        const float4 xv = xh[i];
+        const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma) + c);
+        const uint2 dv = dvv[i];
         const float d0 = __uint_as_float(dv.x << 16), d1 = __uint_as_float(dv.x & 0xffff0000u);
         const float d2 = __uint_as_float(dv.y << 16), d3 = __uint_as_float(dv.y & 0xffff0000u);
         xh[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
-        g[i] = make_float4(d0 * gam[i].x, d1 * gam[i].y, d2 * gam[i].z, d3 * gam[i].w);
+        g[i] = make_float4(d0 * gm.x, d1 * gm.y, d2 * gm.z, d3 * gm.w);
         dg[i].x += d0 * xh[i].x; dg[i].y += d1 * xh[i].y; dg[i].z += d2 * xh[i].z; dg[i].w += d3 * xh[i].w;
         db[i].x += d0; db[i].y += d1; db[i].z += d2; db[i].w += d3;
         s1 += (g[i].x + g[i].y) + (g[i].z + g[i].w);
@@ -126,8 +135,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const bf16* __restri
         float4 o = make_float4(rs * (g[i].x - m1 - xh[i].x * m2), rs * (g[i].y - m1 - xh[i].y * m2),
                                rs * (g[i].z - m1 - xh[i].z * m2), rs * (g[i].w - m1 - xh[i].w * m2));
         if (dres) {
-          const float4 rv = __ldg(reinterpret_cast<const float4*>(dres + pr * ldx) + c);
-          o.x += rv.x; o.y += rv.y; o.z += rv.z; o.w += rv.w;
+          o.x += rv[i].x; o.y += rv[i].y; o.z += rv[i].z; o.w += rv[i].w;
         }
         ds[i].x += o.x; ds[i].y += o.y; ds[i].z += o.z; ds[i].w += o.w;
         if (dx_f32) reinterpret_cast<float4*>(dx_f32 + pr * ldx)[c] = o;
@@ -177,21 +185,35 @@ __global__ void __launch_bounds__(256) colsum_kernel(const void* __restrict__ in
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[j] = 0.f;
   if (c < N) {
-    for (int r = r0 + wy; r < r1; r += 8) {
-      const long long pr = s.row(r);
+    for (int rb = r0 + wy; rb < r1; rb += 32) {  // 4 independent rows per step (volatile: really 4 requests in flight)
       if (F32) {
-        const float4* p = reinterpret_cast<const float4*>((const float*)in + pr * ld + c);
-        const float4 a = __ldg(p), b = __ldg(p + 1);
-        acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
-        acc[4] += b.x; acc[5] += b.y; acc[6] += b.z; acc[7] += b.w;
-      } else {
-        const uint4 v = __ldg(reinterpret_cast<const uint4*>((const bf16*)in + pr * ld + c));
-        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        float4 a[4], b[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          acc[2 * j] += __uint_as_float(w[j] << 16);
-          acc[2 * j + 1] += __uint_as_float(w[j] & 0xffff0000u);
+        for (int u = 0; u < 4; ++u) {
+          const float* p = (const float*)in + s.row(min(rb + 8 * u, r1 - 1)) * ld + c;
+          a[u] = ldv_f4(p);
+          b[u] = ldv_f4(p + 4);
         }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (rb + 8 * u < r1) {
+            acc[0] += a[u].x; acc[1] += a[u].y; acc[2] += a[u].z; acc[3] += a[u].w;
+            acc[4] += b[u].x; acc[5] += b[u].y; acc[6] += b[u].z; acc[7] += b[u].w;
+          }
+      } else {
+        uint4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = ldv_u4((const bf16*)in + s.row(min(rb + 8 * u, r1 - 1)) * ld + c);
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (rb + 8 * u < r1) {
+            const uint32_t w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              acc[2 * j] += __uint_as_float(w[j] << 16);
+              acc[2 * j + 1] += __uint_as_float(w[j] & 0xffff0000u);
+            }
+          }
       }
     }
   }
@@ -340,7 +362,7 @@ extern "C" int bvc_layernorm_bwd(const void* dy, const float* x, int64_t ldx, in
   BVC_CHECK_ARG(M > 0 && d > 0 && d % 4 == 0 && d <= 128 * kLnMaxVec && ldx % 4 == 0 && ldx >= d);
   Seg s{x_seg, x_seg_stride, x_seg_off};
   const int vpl = (d / 4 + 31) / 32;
-  int grid = num_sms() * 2;
+  int grid = num_sms() * (vpl <= 4 ? 2 : 1);  // resident blocks only (register-limited): a 2nd wave would just add tail
   if (grid > (M + 7) / 8) grid = (M + 7) / 8;
   cudaStream_t st = (cudaStream_t)stream;
   const size_t shm = 8 * (size_t)d * sizeof(float);  // [warps][d], <= 32 KB

@@ -326,23 +326,40 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o
 }
 
 // ================================================================================================ backward
-// delta[b,h,s] = sum_d dO[b,s,h,d] * O[b,s,h,d]   (one warp per (b,s,h) row of 64)
+// delta[b,h,s] = sum_d dO[b,s,h,d] * O[b,s,h,d]   (8 lanes per (b,s,h) row of 64, 8 rows per warp step, loads batched)
 __global__ void __launch_bounds__(256) attn_delta_kernel(const bf16* __restrict__ o, const bf16* __restrict__ dout,
                                                          float* __restrict__ delta, long long rows, int S, int H) {
   const int lane = threadIdx.x & 31;
-  const long long stride = (long long)gridDim.x * (blockDim.x >> 5);
-  for (long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < rows; r += stride) {
-    const uint32_t a = __ldg(reinterpret_cast<const uint32_t*>(o + r * 64) + lane);
-    const uint32_t g = __ldg(reinterpret_cast<const uint32_t*>(dout + r * 64) + lane);
-    float s = __uint_as_float(a << 16) * __uint_as_float(g << 16) +
-              __uint_as_float(a & 0xffff0000u) * __uint_as_float(g & 0xffff0000u);
-    s = warp_sum(s);
-    if (lane == 0) {
-      const int hh = (int)(r % H);
-      const long long bs = r / H;
-      const int ss = (int)(bs % S);
-      const long long bb = bs / S;
-      delta[(bb * H + hh) * S + ss] = s;
+  const int sub = lane >> 3, part = lane & 7;
+  const long long warp_id = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long stride = (long long)gridDim.x * (blockDim.x >> 5) * 8;
+  for (long long r0 = warp_id * 8; r0 < rows; r0 += stride) {
+    uint4 a[2], g[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const long long r = min(r0 + u * 4 + sub, rows - 1);
+      a[u] = ldv_u4(o + r * 64 + part * 8);
+      g[u] = ldv_u4(dout + r * 64 + part * 8);
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const uint32_t aw[4] = {a[u].x, a[u].y, a[u].z, a[u].w}, gw[4] = {g[u].x, g[u].y, g[u].z, g[u].w};
+      float sacc = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        sacc += __uint_as_float(aw[j] << 16) * __uint_as_float(gw[j] << 16) +
+                __uint_as_float(aw[j] & 0xffff0000u) * __uint_as_float(gw[j] & 0xffff0000u);
+      sacc += __shfl_xor_sync(0xffffffffu, sacc, 4);
+      sacc += __shfl_xor_sync(0xffffffffu, sacc, 2);
+      sacc += __shfl_xor_sync(0xffffffffu, sacc, 1);
+      const long long r = r0 + u * 4 + sub;
+      if (part == 0 && r < rows) {
+        const int hh = (int)(r % H);
+        const long long bs = r / H;
+        const int ss = (int)(bs % S);
+        const long long bb = bs / S;
+        delta[(bb * H + hh) * S + ss] = sacc;
+      }
     }
   }
 }
@@ -489,21 +506,19 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
     const float* lse_bh = lse + ((long long)b * H + h) * S;
     const float* dl_bh = delta + ((long long)b * H + h) * S;
     // row statistics of query row `qg`: lse in the log2 domain and delta pre-multiplied by the softmax scale
-    // row statistics of query row `qg` (raw: the scaling happens at use, so a prefetch never stalls on its own load)
+    // row statistics of query row `qg`: only the loads here (clamped address); masking and scaling happen at use, so a
+    // prefetch issued one tile ahead never stalls on its own result
     auto load_stats = [&](int qg, float& l_raw, float& d_raw) {
       const int qc = min(qg, S - 1);
       l_raw = __ldg(lse_bh + qc);
       d_raw = __ldg(dl_bh + qc);
-      if (qg >= S) {
-        l_raw = 0.f;
-        d_raw = 0.f;
-      }
     };
     float lse_r, dl_r, lse_n = 0.f, dl_n = 0.f;
     load_stats(MODE_KV ? row : own0 + row, lse_r, dl_r);
     const uint64_t cl2 = pack2(c_log2, c_log2), sc2 = pack2(scale, scale);
     for (int i = 0; i < n_it; ++i) {
       const int kv_valid = MODE_KV ? S - own0 : S - i * kTile;
+      const bool q_ok = (MODE_KV ? i * kTile + row : own0 + row) < S;
       mbar_wait(sdp_full, (uint32_t)i & 1u);
       tc_fence_after();
       uint32_t sv[2][32], dv[2][32];
@@ -516,12 +531,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(sdp_free);
-      if (i > 0) mbar_wait(pds_free, (uint32_t)(i - 1) & 1u);  // previous dV/dK/dQ MMAs finished reading P / dS
-      uint8_t* bP = sP;
-      uint8_t* bD = sD;
-      const float lse2 = lse_r * kLog2e, dls = dl_r * scale;
+      const float lse2 = q_ok ? lse_r * kLog2e : 0.f, dls = q_ok ? dl_r * scale : 0.f;
       const uint64_t nl2 = pack2(-lse2, -lse2), nd2 = pack2(-dls, -dls);
       const bool tail = kv_valid < kTile;
+      // all of this tile's P / dS into registers (packed bf16) first: the math overlaps the previous tile's
+      // dV/dK/dQ MMAs, which are still reading the shared-memory P / dS tiles
+      uint4 pk[8], dk[8];
 #pragma unroll
       for (int c = 0; c < 2; ++c)
 #pragma unroll
@@ -544,18 +559,20 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
             const uint64_t y2 = ffma2(pack2(__uint_as_float(dv[c][j]), __uint_as_float(dv[c][j + 1])), sc2, nd2);
             unpack2(fmul2(pack2(p[t], p[t + 1]), y2), ds[t], ds[t + 1]);
           }
-          const uint32_t off = ptile_chunk_off(row, half * 8 + c * 4 + g);
           if (MODE_KV) {
-            uint4 pk;
-            pk.x = pack_bf16x2(p[0], p[1]); pk.y = pack_bf16x2(p[2], p[3]);
-            pk.z = pack_bf16x2(p[4], p[5]); pk.w = pack_bf16x2(p[6], p[7]);
-            *reinterpret_cast<uint4*>(bP + off) = pk;
+            pk[c * 4 + g].x = pack_bf16x2(p[0], p[1]); pk[c * 4 + g].y = pack_bf16x2(p[2], p[3]);
+            pk[c * 4 + g].z = pack_bf16x2(p[4], p[5]); pk[c * 4 + g].w = pack_bf16x2(p[6], p[7]);
           }
-          uint4 dk;
-          dk.x = pack_bf16x2(ds[0], ds[1]); dk.y = pack_bf16x2(ds[2], ds[3]);
-          dk.z = pack_bf16x2(ds[4], ds[5]); dk.w = pack_bf16x2(ds[6], ds[7]);
-          *reinterpret_cast<uint4*>(bD + off) = dk;
+          dk[c * 4 + g].x = pack_bf16x2(ds[0], ds[1]); dk[c * 4 + g].y = pack_bf16x2(ds[2], ds[3]);
+          dk[c * 4 + g].z = pack_bf16x2(ds[4], ds[5]); dk[c * 4 + g].w = pack_bf16x2(ds[6], ds[7]);
         }
+      if (i > 0) mbar_wait(pds_free, (uint32_t)(i - 1) & 1u);  // previous dV/dK/dQ MMAs finished reading P / dS
+#pragma unroll
+      for (int cg = 0; cg < 8; ++cg) {
+        const uint32_t off = ptile_chunk_off(row, half * 8 + cg);
+        if (MODE_KV) *reinterpret_cast<uint4*>(sP + off) = pk[cg];
+        *reinterpret_cast<uint4*>(sD + off) = dk[cg];
+      }
       fence_async_smem();
       tc_fence_before();
       __syncwarp();
@@ -647,8 +664,8 @@ extern "C" int bvc_attn_bwd(const void* qkv, const void* out, const void* dout, 
   }
   cudaStream_t st = (cudaStream_t)stream;
   const long long rows = (long long)B * S * H;
-  long long g = (rows + 7) / 8;
-  if (g > (long long)num_sms() * 16) g = (long long)num_sms() * 16;
+  long long g = (rows + 63) / 64;
+  if (g > (long long)num_sms() * 8) g = (long long)num_sms() * 8;
   attn_delta_kernel<<<(int)g, 256, 0, st>>>((const bf16*)out, (const bf16*)dout, delta, rows, S, H);
   BVC_CHECK_LAUNCH();
   CUtensorMap tq, td;

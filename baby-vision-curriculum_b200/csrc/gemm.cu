@@ -27,7 +27,14 @@ int gemm_launch_bn128(const bvc_gemm_args* a, int epi, cudaStream_t s);
 int gemm_launch_bn192(const bvc_gemm_args* a, int epi, cudaStream_t s);
 int gemm_launch_bn256(const bvc_gemm_args* a, int epi, cudaStream_t s);
 
-static int pick_block_n(int M, int N) {
+static int pick_block_n(int M, int N, int K, bool wgrad) {
+  // measured on B200 over every shape of the ViT-B step (tools/gpu_gemm_tune.py, profiles/r01_gemm_tune.log)
+  if (wgrad) {
+    if (N % 256 == 0) return 256;
+    if (N % 192 == 0) return 192;
+  } else if (K <= 768 && N % 192 == 0 && N >= 1152) {
+    return 192;  // short-K, epilogue-heavy: three 32-column chunks per warp hand the accumulator back sooner
+  }
   // fewest wasted columns first, then the widest tile (B traffic and MMA efficiency), with at least ~1 wave.
   const int cands[4] = {256, 192, 128, 64};
   int best = 64;
@@ -72,9 +79,9 @@ __global__ void loss_finalize_kernel(const float* __restrict__ partials, long lo
 
 extern "C" int bvc_abi_version(void) { return BVC_ABI_VERSION; }
 
-static int resolve_block_n(int M, int N, int block_n) {
+static int resolve_block_n(int M, int N, int block_n, int K = 1 << 30, bool wgrad = false) {
   if (block_n == 64 || block_n == 128 || block_n == 192 || block_n == 256) return block_n;
-  return bvc::pick_block_n(M, N);
+  return bvc::pick_block_n(M, N, K, wgrad);
 }
 
 extern "C" int64_t bvc_gemm_loss_slots(int32_t M, int32_t N, int32_t block_n) {
@@ -96,7 +103,9 @@ extern "C" int bvc_gemm_bf16(const bvc_gemm_args* a, void* stream) {
   BVC_CHECK_ARG(a->a_mn_major == 0 ? a->lda >= a->K : a->lda >= a->M);
   BVC_CHECK_ARG(a->b_mn_major == 0 ? a->ldb >= a->K : a->ldb >= a->N);
   cudaStream_t s = (cudaStream_t)stream;
-  const int bn = resolve_block_n(a->M, a->N, a->block_n);
+  // loss GEMMs resolve the tile width exactly like bvc_gemm_loss_slots() (which does not know K)
+  const int bn = a->target ? resolve_block_n(a->M, a->N, a->block_n)
+                           : resolve_block_n(a->M, a->N, a->block_n, a->K, a->a_mn_major && a->b_mn_major);
   // pick the leanest epilogue variant that covers the request (gemm_kernel.cuh); anything unusual -> generic
   int epi = bvc::EPI_GENERIC;
   const bool seg = a->out_seg > 0;

@@ -336,9 +336,10 @@ class HeadLossFn(torch.autograd.Function):
         L.layernorm_fwd(xf, nw.detach(), nb.detach(), 1e-5, M, Dd, z, stats[0], stats[1], ldx=Dd, seg=(nm, N, nv))
         diff = _empty((M, K), BF16, dev)
         logits = _empty((M, K), BF16, dev) if want_logits else None
-        part = _empty((L.gemm_loss_slots(M, K, 0),), F32, dev)
+        bn = 192 if K % 192 == 0 else 0  # measured best for the short-K head GEMM (profiles/r01_gemm_tune.log)
+        part = _empty((L.gemm_loss_slots(M, K, bn),), F32, dev)
         L.gemm(z, whb, M, K, Dd, out_bf16=diff, bias=bh.detach(), target=target, ldt=K, loss_partial=part,
-               logits_out=logits)
+               logits_out=logits, block_n=bn)
         loss = _empty((), F32, dev)
         L.loss_finalize(part, float(M) * K, st.status, loss)
         ctx.st, ctx.saved, ctx.dims = st, (xf, stats, z, diff, nw, whb), (M, Dd, K)

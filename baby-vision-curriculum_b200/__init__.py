@@ -13,3 +13,5 @@ from .modeling_videomae import (  # noqa: F401
 )
 from .masking import TubeMaskingGenerator, RandomMaskingGenerator, batch_masks  # noqa: F401
 from .ddputils import AllReduce  # noqa: F401
+from .optim import FusedSGD  # noqa: F401
+from .ddp import DistributedDataParallel  # noqa: F401

@@ -12,7 +12,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libbvc.so")
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 _lib = None
 
@@ -63,6 +63,8 @@ _SIGNATURES = {
                                C.c_void_p]),
     "bvc_attn_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                                C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "bvc_sgd_step": (C.c_int, [C.c_void_p, C.c_int32, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int32,
+                               C.c_void_p, C.c_void_p, C.c_void_p]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 
@@ -299,3 +301,12 @@ def attn_bwd(qkv, out, dout, lse, B, S, H, scale, delta, dqkv):
         _check(load().bvc_attn_bwd(_p(qkv), _p(out), _p(dout), _p(lse), B, S, H, scale, _p(delta), _p(dqkv), _stream()),
                "bvc_attn_bwd")
     _count(3)
+
+
+def sgd_step(table, n_entries, total_elems, lr, momentum, dampening, weight_decay, nesterov, grad_scale, found_inf,
+             bytes_per_elem):
+    _cuda(table, grad_scale, found_inf)
+    with _Timed("sgd_step", 0.0, float(total_elems) * bytes_per_elem):
+        _check(load().bvc_sgd_step(_p(table), n_entries, lr, momentum, dampening, weight_decay, 1 if nesterov else 0,
+                                   _p(grad_scale), _p(found_inf), _stream()), "bvc_sgd_step")
+    _count()

@@ -8,11 +8,16 @@
 // Forward (grid = q-tile x head x clip, 2 CTAs/SM so one CTA's softmax overlaps the other's MMAs):
 //   warp 0 TMA (Q once, K/V ring), warp 1 MMA issuer, warps 2-5 softmax (one query row per thread).
 //   S = Q K^T -> TMEM (128 cols); softmax threads read S, exp2 with a lazily updated running max (rescale O in TMEM
-//   only when the max grows by > 8 in log2 units), write P (bf16) into swizzled smem; O += P V accumulates in TMEM.
+//   only when the max grows by > 8 in log2 units), write P (bf16, packed) back into TMEM as the A operand of
+//   O += P V (tcgen05.mma with A from TMEM): P never touches shared memory, whose bandwidth (128 B/clk/SM, shared
+//   by the UMMA operand reads, the TMA fills and st.shared) is what bounded the shared-memory-P version.
 // Backward (two passes, no atomics, deterministic):
-//   MODE_KV: CTA owns a K/V tile, streams Q/dO tiles:  S, dP = dO V^T, P = exp2(S c - lse), dS = P (dP - delta) scale,
-//            dV += P^T dO, dK += dS^T Q   (P / dS tiles in smem are read MN-major: no transposes anywhere)
-//   MODE_Q : CTA owns a Q/dO tile, streams K/V tiles:  same S, dP, dS;  dQ += dS K.
+//   MODE_KV: CTA owns a K/V tile, streams Q/dO tiles, works on the TRANSPOSED tile (rows = keys):  S^T = K Q^T,
+//            dP^T = V dO^T, P^T = exp2(S^T c - lse_q), dS^T = P^T (dP^T - delta_q) scale,  dV += P^T dO, dK += dS^T Q
+//   MODE_Q : CTA owns a Q/dO tile, streams K/V tiles:  S = Q K^T, dP = dO V^T, same P / dS;  dQ += dS K.
+//   In both passes P / dS go back to TMEM (packed bf16) and feed the accumulating MMAs as A-from-TMEM operands.
+#include <type_traits>
+
 #include "../../include/bvc.h"
 #include "bvc_host.h"
 #include "bvc_ptx.cuh"
@@ -89,7 +94,7 @@ __device__ __forceinline__ uint32_t ptile_chunk_off(int row, int chunk16 /*0..15
 
 // ================================================================================================ forward
 constexpr int kFwdThreads = 192;
-constexpr int kFwdSmem = kTileBytes * (1 + 2 + 2) + 2 * kTileBytes + 128;  // Q, K[2], V[2], P(32 KB), barriers
+constexpr int kFwdSmem = kTileBytes * (1 + 2 + 2) + 128;  // Q, K[2], V[2], barriers
 
 __global__ void __launch_bounds__(kFwdThreads, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ out, float* __restrict__ lse, int S,
@@ -98,8 +103,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o
   uint8_t* sQ = smem;
   uint8_t* sK = smem + kTileBytes;          // 2 stages
   uint8_t* sV = smem + 3 * kTileBytes;      // 2 stages
-  uint8_t* sP = smem + 5 * kTileBytes;      // 32 KB
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 7 * kTileBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 5 * kTileBytes);
   uint64_t* q_full = bars + 0;
   uint64_t* k_full = bars + 1;    // [2]   K and V have separate rings: a K stage is released as soon as its
   uint64_t* k_empty = bars + 3;   // [2]   S = Q K^T MMA has run (long before the P V MMA of the same tile), which
@@ -136,7 +140,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tS = tmem_base, tO = tmem_base + 128;
+  const uint32_t tS = tmem_base, tO = tmem_base + 128, tP = tmem_base + 192;  // P: [128][128] bf16 = 64 columns
 
   if (warp == 0) {
     if (lane == 0) {
@@ -154,39 +158,58 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc_s = umma_idesc_bf16(128, 0, 0, 128);
-      constexpr uint32_t idesc_o = umma_idesc_bf16(64, 0, 1, 128);
-      const uint32_t aQ = smem_u32(sQ), aP = smem_u32(sP);
-      mbar_wait(q_full, 0);
-      mbar_wait(&k_full[0], 0);
-      tc_fence_after();
+    // MMA issuer: warp-uniform control flow, one elected lane issues (see elect_one in bvc_ptx.cuh)
+    constexpr uint32_t idesc_o = umma_idesc_bf16(64, 0, 1, 128);
+    const uint64_t dQ = desc_k(smem_u32(sQ), 0);
+    // the last K/V tile of a sequence is ragged (1568 = 12 x 128 + 32; 160 = 128 + 32): size its MMAs to the valid
+    // rows rounded up to 16 (N of S = Q K^T, K-steps of O += P V) instead of paying for a full 128
+    auto n_valid16 = [&](int j) { return min(kTile, (S - j * kTile + 15) & ~15); };
+    mbar_wait(q_full, 0);
+    mbar_wait(&k_full[0], 0);
+    tc_fence_after();
+    if (elect_one()) {
+      const uint64_t dK = desc_k(smem_u32(sK), 0);
+      const uint32_t idesc_s = umma_idesc_bf16(n_valid16(0), 0, 0, 128);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) umma_bf16_ss(tS, desc_k(aQ, k), desc_k(smem_u32(sK), k), idesc_s, k > 0);
+      for (int k = 0; k < 4; ++k) umma_bf16_ss(tS, dQ + 2 * k, dK + 2 * k, idesc_s, k > 0);
       umma_commit(s_full);
       umma_commit(&k_empty[0]);
-      for (int j = 0; j < n_kv; ++j) {
-        if (j + 1 < n_kv) {
-          const int st = (j + 1) & 1;
-          mbar_wait(&k_full[st], (uint32_t)((j + 1) >> 1) & 1u);
-          mbar_wait(s_free, (uint32_t)j & 1u);
-          tc_fence_after();
-          const uint32_t aK = smem_u32(sK + st * kTileBytes);
+    }
+    __syncwarp();
+    for (int j = 0; j < n_kv; ++j) {
+      if (j + 1 < n_kv) {
+        const int st = (j + 1) & 1;
+        mbar_wait(&k_full[st], (uint32_t)((j + 1) >> 1) & 1u);
+        mbar_wait(s_free, (uint32_t)j & 1u);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint64_t dK = desc_k(smem_u32(sK + st * kTileBytes), 0);
+          const uint32_t idesc_s = umma_idesc_bf16(n_valid16(j + 1), 0, 0, 128);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_bf16_ss(tS, desc_k(aQ, k), desc_k(aK, k), idesc_s, k > 0);
+          for (int k = 0; k < 4; ++k) umma_bf16_ss(tS, dQ + 2 * k, dK + 2 * k, idesc_s, k > 0);
           umma_commit(s_full);
           umma_commit(&k_empty[st]);
         }
-        mbar_wait(&v_full[j & 1], (uint32_t)(j >> 1) & 1u);
-        mbar_wait(p_full, (uint32_t)j & 1u);
-        tc_fence_after();
-        const uint32_t aV = smem_u32(sV + (j & 1) * kTileBytes);
+        __syncwarp();
+      }
+      mbar_wait(&v_full[j & 1], (uint32_t)(j >> 1) & 1u);
+      mbar_wait(p_full, (uint32_t)j & 1u);
+      tc_fence_after();
+      const int ksteps = n_valid16(j) >> 4;
+      if (elect_one()) {
+        // O += P V : A = P (TMEM, packed bf16, 8 columns per K = 16 step), B = V_j (MN-major: n = d, k = kv)
+        const uint64_t dV = desc_mn(smem_u32(sV + (j & 1) * kTileBytes), 0, 8192);
+        const uint32_t acc0 = j > 0;
+        if (ksteps == 8) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k)
-          umma_bf16_ss(tO, desc_k(aP + (k >> 2) * kTileBytes, k & 3), desc_mn(aV, k, 8192), idesc_o, (j > 0 || k > 0));
+          for (int k = 0; k < 8; ++k) umma_bf16_ts(tO, tP + k * 8, dV + 128 * k, idesc_o, acc0 | (k > 0));
+        } else {
+          for (int k = 0; k < ksteps; ++k) umma_bf16_ts(tO, tP + k * 8, dV + 128 * k, idesc_o, acc0 | (k > 0));
+        }
         umma_commit(o_full);
         umma_commit(&v_empty[j & 1]);
       }
+      __syncwarp();
     }
   } else {
     const int q = warp & 3;
@@ -257,6 +280,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o
           __syncwarp();
           if (lane == 0) mbar_arrive(s_free);
         }
+        uint32_t pk[32];  // this thread's 64 probabilities of the half-row, packed bf16x2
 #pragma unroll
         for (int c = 0; c < 2; ++c)
 #pragma unroll
@@ -277,17 +301,18 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o
               }
               lsum2 = fadd2(lsum2, pack2(p[i], p[i + 1]));
             }
-            uint4 pk;
-            pk.x = pack_bf16x2(p[0], p[1]); pk.y = pack_bf16x2(p[2], p[3]);
-            pk.z = pack_bf16x2(p[4], p[5]); pk.w = pack_bf16x2(p[6], p[7]);
-            *reinterpret_cast<uint4*>(sP + ptile_chunk_off(row, hh * 8 + c * 4 + g)) = pk;
+            pk[c * 16 + g * 4 + 0] = pack_bf16x2(p[0], p[1]);
+            pk[c * 16 + g * 4 + 1] = pack_bf16x2(p[2], p[3]);
+            pk[c * 16 + g * 4 + 2] = pack_bf16x2(p[4], p[5]);
+            pk[c * 16 + g * 4 + 3] = pack_bf16x2(p[6], p[7]);
           }
+        tmem_st_32x32b_x32(tP + lane_base + hh * 32, pk);
       }
       float lsum, lsum_hi;
       unpack2(lsum2, lsum, lsum_hi);
       lsum += lsum_hi;
       l += lsum;
-      fence_async_smem();
+      tmem_st_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full);
@@ -364,11 +389,19 @@ __global__ void __launch_bounds__(256) attn_delta_kernel(const bf16* __restrict_
   }
 }
 
-constexpr int kBwdThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2-9 compute
+// warpgroup 0: warp 0 TMA, warp 1 MMA, warps 2-3 idle; warpgroups 1-2 (warps 4-11): compute.  Launched at the 168
+// registers/thread that 384 threads allow, then warpgroup 0 shrinks to 88 and the compute warpgroups grow to 208
+// (setmaxnreg): the compute threads hold a 64-wide slice of S and dP plus their packed P / dS outputs in registers.
+constexpr int kBwdThreads = 384;
+constexpr int kBwdRegsCtl = 88, kBwdRegsCompute = 208;
 // resident pair (2 tiles) + stream ring (4 stages x 2 tiles: the streamed tiles' TMA latency was the critical path
-// with 2 stages -- ncu: 30 % of the compute warps' samples waiting for S/dP) + P (32 KB) + dS (32 KB) + barriers
+// with 2 stages -- ncu: 30 % of the compute warps' samples waiting for S/dP) + per-column statistics ring + barriers.
+// P / dS never touch shared memory: they go back into TMEM (packed bf16) as the A operands of the accumulating MMAs.
+// With P / dS staged in shared memory the kernel was bound by the shared-memory port (per 128x128 tile pair: 160 KB of
+// UMMA operand reads + 64 KB st.shared + 32 KB TMA fill = 2048 clk at 128 B/clk against 1024 clk of tensor work).
 constexpr int kBwdStages = 4;
-constexpr int kBwdSmem = kTileBytes * (2 + 2 * kBwdStages) + 4 * kTileBytes + 256;
+constexpr int kBwdStatBytes = 2 * 2 * kTile * 4;  // [2 buffers][nl2 | nds][128] fp32
+constexpr int kBwdSmem = kTileBytes * (2 + 2 * kBwdStages) + kBwdStatBytes + 256;
 
 template <int MODE_KV>
 __global__ void __launch_bounds__(kBwdThreads, 1)
@@ -380,9 +413,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
   uint8_t* sR1 = smem + kTileBytes;        // MODE_KV: V_j    | MODE_Q: dO_i
   uint8_t* sX = smem + 2 * kTileBytes;                     // [stages] MODE_KV: Q_i  | MODE_Q: K_j
   uint8_t* sY = smem + (2 + kBwdStages) * kTileBytes;      // [stages] MODE_KV: dO_i | MODE_Q: V_j
-  uint8_t* sP = smem + (2 + 2 * kBwdStages) * kTileBytes;  // 32 KB (MODE_KV only)
-  uint8_t* sD = sP + 2 * kTileBytes;                       // 32 KB dS
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sD + 2 * kTileBytes);
+  float* sStat = reinterpret_cast<float*>(smem + (2 + 2 * kBwdStages) * kTileBytes);  // MODE_KV only
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (2 + 2 * kBwdStages) * kTileBytes + kBwdStatBytes);
   uint64_t* r_full = bars + 0;
   uint64_t* st_full = bars + 1;                  // [stages]
   uint64_t* st_empty = bars + 1 + kBwdStages;    // [stages]
@@ -416,8 +448,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // fp32 [128 lanes][128]: scores and dP; fp32 [128][64]: accumulators; packed bf16 [128][128] = 64 columns: P, dS
   const uint32_t tS = tmem_base, tDP = tmem_base + 128, tA0 = tmem_base + 256, tA1 = tmem_base + 320;
+  const uint32_t tP = tmem_base + 384, tDS = tmem_base + 448;
 
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kBwdRegsCtl));
   if (warp == 0) {
     if (lane == 0) {
       mbar_expect_tx(r_full, 2 * kTileBytes);
@@ -442,83 +478,115 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc_s = umma_idesc_bf16(128, 0, 0, 128);
-      constexpr uint32_t idesc_tt = umma_idesc_bf16(64, 1, 1, 128);  // A MN-major, B MN-major (dV, dK)
-      constexpr uint32_t idesc_q = umma_idesc_bf16(64, 0, 1, 128);   // A K-major, B MN-major (dQ)
-      const uint32_t aR0 = smem_u32(sR0), aR1 = smem_u32(sR1);
-      auto issue_s_dp = [&](int st) {
-        const uint32_t aX = smem_u32(sX + st * kTileBytes), aY = smem_u32(sY + st * kTileBytes);
-        // S = Q K^T, dP = dO V^T  (rows = q, cols = kv)
-        const uint32_t q_t = MODE_KV ? aX : aR0, k_t = MODE_KV ? aR0 : aX;
-        const uint32_t do_t = MODE_KV ? aY : aR1, v_t = MODE_KV ? aR1 : aY;
+    // MMA issuer: the whole warp walks the (uniform) control flow and polls the barriers, one elected lane issues
+    constexpr uint32_t idesc_acc = umma_idesc_bf16(64, 0, 1, 128);  // A from TMEM (K-major), B MN-major, N = 64
+    // k = 0 descriptors; a K = 16 step moves the start address by 32 B (K-major, +2 in the descriptor's 16-byte
+    // units) or by 16 rows = 2048 B (MN-major, +128)
+    const uint64_t dR0 = desc_k(smem_u32(sR0), 0), dR1 = desc_k(smem_u32(sR1), 0);
+    // ragged last tile of the STREAMED operand: it is the N of the score MMAs in both modes (MODE_KV streams the
+    // query tiles and computes S^T = K Q^T; MODE_Q streams the K/V tiles and computes S = Q K^T) and the reduction
+    // dimension of the accumulating MMAs, so both shrink to its valid rows rounded up to 16
+    auto valid16 = [&](int t0) { return min(kTile, (S - t0 + 15) & ~15); };
+    auto issue_s_dp = [&](int st, int it) {
+      const uint32_t idesc_s = umma_idesc_bf16(valid16(it * kTile), 0, 0, 128);
+      const uint64_t dX = desc_k(smem_u32(sX + st * kTileBytes), 0), dY = desc_k(smem_u32(sY + st * kTileBytes), 0);
+      // MODE_KV: S^T = K Q^T, dP^T = V dO^T (rows = kv, cols = q);  MODE_Q: S = Q K^T, dP = dO V^T (rows = q)
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16_ss(tS, desc_k(q_t, k), desc_k(k_t, k), idesc_s, k > 0);
+      for (int k = 0; k < 4; ++k) umma_bf16_ss(tS, dR0 + 2 * k, dX + 2 * k, idesc_s, k > 0);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16_ss(tDP, desc_k(do_t, k), desc_k(v_t, k), idesc_s, k > 0);
-      };
-      mbar_wait(r_full, 0);
-      mbar_wait(&st_full[0], 0);
-      tc_fence_after();
-      issue_s_dp(0);
+      for (int k = 0; k < 4; ++k) umma_bf16_ss(tDP, dR1 + 2 * k, dY + 2 * k, idesc_s, k > 0);
+    };
+    mbar_wait(r_full, 0);
+    mbar_wait(&st_full[0], 0);
+    tc_fence_after();
+    if (elect_one()) {
+      issue_s_dp(0, 0);
       umma_commit(sdp_full);
-      for (int i = 0; i < n_it; ++i) {
-        if (i + 1 < n_it) {
-          const int st = (i + 1) % kBwdStages;
-          mbar_wait(&st_full[st], (uint32_t)((i + 1) / kBwdStages) & 1u);
-          mbar_wait(sdp_free, (uint32_t)i & 1u);
-          tc_fence_after();
-          issue_s_dp(st);
+    }
+    __syncwarp();
+    for (int i = 0; i < n_it; ++i) {
+      if (i + 1 < n_it) {
+        const int st = (i + 1) % kBwdStages;
+        mbar_wait(&st_full[st], (uint32_t)((i + 1) / kBwdStages) & 1u);
+        mbar_wait(sdp_free, (uint32_t)i & 1u);
+        tc_fence_after();
+        if (elect_one()) {
+          issue_s_dp(st, i + 1);
           umma_commit(sdp_full);
         }
-        mbar_wait(pds_full, (uint32_t)i & 1u);
-        tc_fence_after();
-        const int cst = i % kBwdStages;
-        const uint32_t aX = smem_u32(sX + cst * kTileBytes), aY = smem_u32(sY + cst * kTileBytes);
-        const uint32_t aP = smem_u32(sP), aD = smem_u32(sD);
+        __syncwarp();
+      }
+      mbar_wait(pds_full, (uint32_t)i & 1u);
+      tc_fence_after();
+      const int cst = i % kBwdStages;
+      const int ksteps = valid16(i * kTile) >> 4;  // streamed tile = the reduction dimension in both modes
+      if (elect_one()) {
+        const uint64_t dX = desc_mn(smem_u32(sX + cst * kTileBytes), 0, 8192);
+        const uint64_t dY = desc_mn(smem_u32(sY + cst * kTileBytes), 0, 8192);
+        const uint32_t acc0 = i > 0;
         if (MODE_KV) {
-          // dV[kv, d] += P^T dO : A = P (MN-major: m = kv, k = q), B = dO_i (MN-major: n = d, k = q)
+          // dV[kv, d] += P^T dO : A = P^T (TMEM, m = kv, k = q), B = dO_i (MN-major: n = d, k = q)
+          // dK[kv, d] += dS^T Q : A = dS^T (TMEM), B = Q_i (MN-major)
+          if (ksteps == 8) {
 #pragma unroll
-          for (int k = 0; k < 8; ++k)
-            umma_bf16_ss(tA0, desc_mn(aP, k, kTileBytes), desc_mn(aY, k, 8192), idesc_tt, (i > 0 || k > 0));
-          // dK[kv, d] += dS^T Q
+            for (int k = 0; k < 8; ++k) umma_bf16_ts(tA0, tP + k * 8, dY + 128 * k, idesc_acc, acc0 | (k > 0));
 #pragma unroll
-          for (int k = 0; k < 8; ++k)
-            umma_bf16_ss(tA1, desc_mn(aD, k, kTileBytes), desc_mn(aX, k, 8192), idesc_tt, (i > 0 || k > 0));
+            for (int k = 0; k < 8; ++k) umma_bf16_ts(tA1, tDS + k * 8, dX + 128 * k, idesc_acc, acc0 | (k > 0));
+          } else {
+            for (int k = 0; k < ksteps; ++k) umma_bf16_ts(tA0, tP + k * 8, dY + 128 * k, idesc_acc, acc0 | (k > 0));
+            for (int k = 0; k < ksteps; ++k) umma_bf16_ts(tA1, tDS + k * 8, dX + 128 * k, idesc_acc, acc0 | (k > 0));
+          }
         } else {
-          // dQ[q, d] += dS K : A = dS (K-major: m = q, k = kv), B = K_j (MN-major: n = d, k = kv)
+          // dQ[q, d] += dS K : A = dS (TMEM, m = q, k = kv), B = K_j (MN-major: n = d, k = kv)
+          if (ksteps == 8) {
 #pragma unroll
-          for (int k = 0; k < 8; ++k)
-            umma_bf16_ss(tA0, desc_k(aD + (k >> 2) * kTileBytes, k & 3), desc_mn(aX, k, 8192), idesc_q,
-                         (i > 0 || k > 0));
+            for (int k = 0; k < 8; ++k) umma_bf16_ts(tA0, tDS + k * 8, dX + 128 * k, idesc_acc, acc0 | (k > 0));
+          } else {
+            for (int k = 0; k < ksteps; ++k) umma_bf16_ts(tA0, tDS + k * 8, dX + 128 * k, idesc_acc, acc0 | (k > 0));
+          }
         }
         umma_commit(pds_free);
         umma_commit(&st_empty[cst]);
       }
+      __syncwarp();
     }
+  }
   } else {
-    const int e = warp - 2;
-    const int q = warp & 3;
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kBwdRegsCompute));
+    // 8 compute warps: TMEM lane quadrant q4 = warp % 4 (rows q4*32 .. +31 of the score tile), column half = (warp-4)/4.
+    // MODE_Q : row = query, columns = keys;   statistics (lse, delta) are per ROW: two registers per thread.
+    // MODE_KV: row = key,   columns = queries; statistics are per COLUMN: staged in shared memory per streamed tile.
+    // No masking anywhere: rows / columns past the end of the sequence meet zero-filled operand rows in every MMA
+    // that consumes them (or land in accumulator rows that are never stored); they only have to stay finite, which
+    // the clamped statistics loads guarantee.
+    const int e = warp - 4;
+    const int q4 = warp & 3;
     const int half = e >> 2;
-    const int row = q * 32 + lane;  // S / dP row = query index within the tile
-    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    const int row = q4 * 32 + lane;
+    const int ct = threadIdx.x - 128;  // 0..255
+    const uint32_t lane_base = (uint32_t)(q4 * 32) << 16;
     const float c_log2 = scale * kLog2e;
     const float* lse_bh = lse + ((long long)b * H + h) * S;
     const float* dl_bh = delta + ((long long)b * H + h) * S;
-    // row statistics of query row `qg`: lse in the log2 domain and delta pre-multiplied by the softmax scale
-    // row statistics of query row `qg`: only the loads here (clamped address); masking and scaling happen at use, so a
-    // prefetch issued one tile ahead never stalls on its own result
-    auto load_stats = [&](int qg, float& l_raw, float& d_raw) {
-      const int qc = min(qg, S - 1);
-      l_raw = __ldg(lse_bh + qc);
-      d_raw = __ldg(dl_bh + qc);
-    };
-    float lse_r, dl_r, lse_n = 0.f, dl_n = 0.f;
-    load_stats(MODE_KV ? row : own0 + row, lse_r, dl_r);
     const uint64_t cl2 = pack2(c_log2, c_log2), sc2 = pack2(scale, scale);
+    // MODE_KV: compute thread ct stages statistic (ct < 128 ? -lse*log2e : -delta*scale) of query ct % 128
+    auto load_stat = [&](int it) {
+      const int qg = min(it * kTile + (ct & 127), S - 1);
+      return __ldg((ct < 128 ? lse_bh : dl_bh) + qg);
+    };
+    auto put_stat = [&](int it, float v) { sStat[(it & 1) * 2 * kTile + ct] = ct < 128 ? -v * kLog2e : -v * scale; };
+    float st_next = 0.f;
+    uint64_t nl2 = 0, nd2 = 0;
+    if (MODE_KV) {
+      put_stat(0, load_stat(0));
+      if (n_it > 1) st_next = load_stat(1);
+    } else {
+      const int qc = min(own0 + row, S - 1);
+      const float l = -__ldg(lse_bh + qc) * kLog2e, d = -__ldg(dl_bh + qc) * scale;
+      nl2 = pack2(l, l);
+      nd2 = pack2(d, d);
+    }
     for (int i = 0; i < n_it; ++i) {
-      const int kv_valid = MODE_KV ? S - own0 : S - i * kTile;
-      const bool q_ok = (MODE_KV ? i * kTile + row : own0 + row) < S;
       mbar_wait(sdp_full, (uint32_t)i & 1u);
       tc_fence_after();
       uint32_t sv[2][32], dv[2][32];
@@ -526,61 +594,61 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
       for (int c = 0; c < 2; ++c) tmem_ld_32x32b_x32(tS + lane_base + half * 64 + c * 32, sv[c]);
 #pragma unroll
       for (int c = 0; c < 2; ++c) tmem_ld_32x32b_x32(tDP + lane_base + half * 64 + c * 32, dv[c]);
-      if (MODE_KV && i + 1 < n_it) load_stats((i + 1) * kTile + row, lse_n, dl_n);  // in flight during this tile
-      tmem_ld_wait();
+      // all four loads landed before the TMEM columns are handed back (the math below must not be hoisted between
+      // the loads: that delays sdp_free, and with it the next tile's S / dP MMAs, by half a tile of MUFU work)
+      tmem_ld_wait_pin(sv[0]);
+      tmem_ld_wait_pin(sv[1]);
+      tmem_ld_wait_pin(dv[0]);
+      tmem_ld_wait_pin(dv[1]);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(sdp_free);
-      const float lse2 = q_ok ? lse_r * kLog2e : 0.f, dls = q_ok ? dl_r * scale : 0.f;
-      const uint64_t nl2 = pack2(-lse2, -lse2), nd2 = pack2(-dls, -dls);
-      const bool tail = kv_valid < kTile;
-      // all of this tile's P / dS into registers (packed bf16) first: the math overlaps the previous tile's
-      // dV/dK/dQ MMAs, which are still reading the shared-memory P / dS tiles
-      uint4 pk[8], dk[8];
+      if (MODE_KV) {
+        // every compute warp is past tile i-1's math (which read buffer (i+1)&1) and tile i's statistics are visible
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (i + 1 < n_it) {
+          put_stat(i + 1, st_next);
+          if (i + 2 < n_it) st_next = load_stat(i + 2);
+        }
+      }
+      const float* st_l = sStat + (i & 1) * 2 * kTile + half * 64;
+      const float* st_d = st_l + kTile;
+      // this thread's 64 P / dS values of the tile, packed bf16x2; the math overlaps the previous tile's accumulating
+      // MMAs, which are still reading the TMEM P / dS operands
+      uint32_t pk[32], dk[32];
 #pragma unroll
       for (int c = 0; c < 2; ++c)
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
-          float p[8], ds[8];
 #pragma unroll
           for (int t = 0; t < 8; t += 2) {
             const int j = g * 8 + t;
-            const uint64_t x2 = ffma2(pack2(__uint_as_float(sv[c][j]), __uint_as_float(sv[c][j + 1])), cl2, nl2);
+            // per-column statistics: one 8-byte broadcast load yields the packed pair directly
+            const uint64_t nlp = MODE_KV ? *reinterpret_cast<const uint64_t*>(st_l + c * 32 + j) : nl2;
+            const uint64_t ndp = MODE_KV ? *reinterpret_cast<const uint64_t*>(st_d + c * 32 + j) : nd2;
+            // P = exp2(S * scale * log2e - lse * log2e)
+            const uint64_t x2 = ffma2(pack2(__uint_as_float(sv[c][j]), __uint_as_float(sv[c][j + 1])), cl2, nlp);
             float a0, a1;
             unpack2(x2, a0, a1);
-            p[t] = exp2f(a0);
-            p[t + 1] = exp2f(a1);
-            if (tail) {  // warp-uniform: only the last K/V tile of the sequence has columns past the end
-              const int col = half * 64 + c * 32 + j;
-              if (col >= kv_valid) p[t] = 0.f;
-              if (col + 1 >= kv_valid) p[t + 1] = 0.f;
-            }
+            const float p0 = exp2f(a0), p1 = exp2f(a1);
             // dS = P * (dP - delta) * scale
-            const uint64_t y2 = ffma2(pack2(__uint_as_float(dv[c][j]), __uint_as_float(dv[c][j + 1])), sc2, nd2);
-            unpack2(fmul2(pack2(p[t], p[t + 1]), y2), ds[t], ds[t + 1]);
+            const uint64_t y2 = ffma2(pack2(__uint_as_float(dv[c][j]), __uint_as_float(dv[c][j + 1])), sc2, ndp);
+            float d0, d1;
+            unpack2(fmul2(pack2(p0, p1), y2), d0, d1);
+            if (MODE_KV) pk[c * 16 + g * 4 + (t >> 1)] = pack_bf16x2(p0, p1);
+            dk[c * 16 + g * 4 + (t >> 1)] = pack_bf16x2(d0, d1);
           }
-          if (MODE_KV) {
-            pk[c * 4 + g].x = pack_bf16x2(p[0], p[1]); pk[c * 4 + g].y = pack_bf16x2(p[2], p[3]);
-            pk[c * 4 + g].z = pack_bf16x2(p[4], p[5]); pk[c * 4 + g].w = pack_bf16x2(p[6], p[7]);
-          }
-          dk[c * 4 + g].x = pack_bf16x2(ds[0], ds[1]); dk[c * 4 + g].y = pack_bf16x2(ds[2], ds[3]);
-          dk[c * 4 + g].z = pack_bf16x2(ds[4], ds[5]); dk[c * 4 + g].w = pack_bf16x2(ds[6], ds[7]);
         }
-      if (i > 0) mbar_wait(pds_free, (uint32_t)(i - 1) & 1u);  // previous dV/dK/dQ MMAs finished reading P / dS
-#pragma unroll
-      for (int cg = 0; cg < 8; ++cg) {
-        const uint32_t off = ptile_chunk_off(row, half * 8 + cg);
-        if (MODE_KV) *reinterpret_cast<uint4*>(sP + off) = pk[cg];
-        *reinterpret_cast<uint4*>(sD + off) = dk[cg];
+      if (i > 0) {
+        mbar_wait(pds_free, (uint32_t)(i - 1) & 1u);  // previous dV/dK/dQ MMAs finished reading P / dS
+        tc_fence_after();
       }
-      fence_async_smem();
+      if (MODE_KV) tmem_st_32x32b_x32(tP + lane_base + half * 32, pk);
+      tmem_st_32x32b_x32(tDS + lane_base + half * 32, dk);
+      tmem_st_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(pds_full);
-      if (MODE_KV) {
-        lse_r = lse_n;
-        dl_r = dl_n;
-      }
     }
     // epilogue: the accumulators (rows = owned tile rows, 64 cols); this warp writes 32 of the 64 columns
     mbar_wait(pds_free, (uint32_t)(n_it - 1) & 1u);
@@ -595,12 +663,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
         bf16* dst = dqkv + ((tok * 3 + which) * H + h) * 64 + half * 32;
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
-          uint4 pk;
-          pk.x = pack_bf16x2(__uint_as_float(ov[g * 8 + 0]), __uint_as_float(ov[g * 8 + 1]));
-          pk.y = pack_bf16x2(__uint_as_float(ov[g * 8 + 2]), __uint_as_float(ov[g * 8 + 3]));
-          pk.z = pack_bf16x2(__uint_as_float(ov[g * 8 + 4]), __uint_as_float(ov[g * 8 + 5]));
-          pk.w = pack_bf16x2(__uint_as_float(ov[g * 8 + 6]), __uint_as_float(ov[g * 8 + 7]));
-          *reinterpret_cast<uint4*>(dst + g * 8) = pk;
+          uint4 o4;
+          o4.x = pack_bf16x2(__uint_as_float(ov[g * 8 + 0]), __uint_as_float(ov[g * 8 + 1]));
+          o4.y = pack_bf16x2(__uint_as_float(ov[g * 8 + 2]), __uint_as_float(ov[g * 8 + 3]));
+          o4.z = pack_bf16x2(__uint_as_float(ov[g * 8 + 4]), __uint_as_float(ov[g * 8 + 5]));
+          o4.w = pack_bf16x2(__uint_as_float(ov[g * 8 + 6]), __uint_as_float(ov[g * 8 + 7]));
+          *reinterpret_cast<uint4*>(dst + g * 8) = o4;
         }
       }
     };

@@ -171,6 +171,18 @@ __device__ __forceinline__ void umma_bf16_ss(uint32_t tmem_d, uint64_t desc_a, u
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// D[tmem] (+)= A[tmem] * B[smem]: A is a K-major [128 lanes][K] bf16 tile packed two elements per 32-bit TMEM column
+// (element k of row m at lane m, column k/2, low half = even k); 8 columns per K = 16 step.  Keeps the A operand
+// (softmax probabilities, dS) off the shared-memory port, which is what bounds the attention kernels.
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // mbarrier arrive when every tcgen05 op previously issued by this thread has completed
 // (implies tcgen05.fence::before_thread_sync).
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
@@ -201,6 +213,27 @@ __device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&v)
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// tcgen05.wait::ld that also names the loaded registers as read-write operands: nothing that consumes them can be
+// scheduled above the wait, and nothing after the wait (e.g. the mbarrier arrive that hands the TMEM columns back
+// to the MMA warp) can be sunk below the consumers' math by the compiler's scheduler.
+__device__ __forceinline__ void tmem_ld_wait_pin(uint32_t (&v)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
+                 "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]),
+                 "+r"(v[16]), "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]),
+                 "+r"(v[23]), "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]),
+                 "+r"(v[30]), "+r"(v[31])
+               :
+               : "memory");
+}
+// one lane of the (converged) warp; the tcgen05.mma / commit issuer.  Keeping the surrounding control flow
+// warp-uniform (instead of `if (lane == 0) { ...whole loop... }`) lets ptxas keep descriptors and loop state in
+// uniform registers: the single-lane version spent ~16 instructions (R2UR, re-masking, an ELECT retry loop) per MMA.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 
 // ----------------------------------------------------------------------------------------------
 // UMMA descriptors (bit layout: cute/arch/mma_sm100_desc.hpp in the CUTLASS tree, PTX ISA "tcgen05

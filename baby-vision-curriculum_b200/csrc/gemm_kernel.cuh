@@ -160,42 +160,51 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(BN, A_MN, B_MN, BM);
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
-        const int split = w % p.k_splits;
-        const int kb0 = split * p.kb_per_split;
-        const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
-        mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
+    // MMA issuer.  The whole warp walks the warp-uniform control flow and polls the barriers; one elected lane issues
+    // the tcgen05 instructions.  (With the entire loop under `if (lane == 0)` ptxas kept the loop state in vector
+    // registers and spent ~16 instructions -- R2UR moves, descriptor re-masking, an ELECT retry loop -- per MMA,
+    // more than a 128 x N x 16 MMA takes to execute for N <= 192.)
+    constexpr uint32_t idesc = umma_idesc_bf16(BN, A_MN, B_MN, BM);
+    // descriptor start-address step of one K = 16 slice, in 16-byte units: 2048 B (MN-major) or 32 B (K-major)
+    constexpr uint64_t kStepA = A_MN ? 128 : 2, kStepB = B_MN ? 128 : 2;
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+      const int split = w % p.k_splits;
+      const int kb0 = split * p.kb_per_split;
+      const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+      mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-        for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
+        if (elect_one()) {
           const uint32_t a_addr = smem_u32(smem + stage * Cfg::kStageBytes);
           const uint32_t b_addr = a_addr + Cfg::kABytes;
+          const uint64_t da = A_MN ? umma_smem_desc(a_addr, 1024, 8192) : umma_smem_desc(a_addr, 1024, 16);
+          const uint64_t db = B_MN ? umma_smem_desc(b_addr, 1024, 8192) : umma_smem_desc(b_addr, 1024, 16);
+          const uint32_t acc0 = kb > kb0;
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            const uint64_t da = A_MN ? umma_smem_desc(a_addr + k * 2048, 1024, 8192)
-                                     : umma_smem_desc(a_addr + k * 32, 1024, 16);
-            const uint64_t db = B_MN ? umma_smem_desc(b_addr + k * 2048, 1024, 8192)
-                                     : umma_smem_desc(b_addr + k * 32, 1024, 16);
-            umma_bf16_ss(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-          }
+          for (int k = 0; k < BK / 16; ++k)
+            umma_bf16_ss(d_tmem, da + kStepA * k, db + kStepB * k, idesc, acc0 | (k > 0));
           umma_commit(&empty_bar[stage]);
-          if (++stage == Cfg::kStages) {
-            stage = 0;
-            phase ^= 1u;
-          }
+          if (kb + 1 == kb1) umma_commit(&tmem_full[acc]);
         }
-        umma_commit(&tmem_full[acc]);
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1u;
+        __syncwarp();
+        if (++stage == Cfg::kStages) {
+          stage = 0;
+          phase ^= 1u;
+        }
       }
+      if (kb0 >= kb1) {  // empty K range (never produced by the host-side split choice): keep the protocol alive
+        if (elect_one()) umma_commit(&tmem_full[acc]);
+        __syncwarp();
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
     }
   } else {
     // ---------------------------------------------------------------- epilogue warps

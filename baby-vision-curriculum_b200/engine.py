@@ -81,6 +81,7 @@ class Bf16Cache:
         table = torch.from_numpy(tab).to(device)
         self._plan = (sig, table, len(rows), total, views, wbuf, bbuf)
         self._versions = None
+        self._shadow = {id(src): (dp, f) for src, (_, dp, _, f) in zip(self._params, rows)}
 
     def refresh(self):
         ver = tuple(p._version for p in self._params)
@@ -88,6 +89,18 @@ class Bf16Cache:
             _, table, n, total, _, _, _ = self._plan
             L.cast_multi(table, n, total)
             self._versions = ver
+
+    def shadows(self):
+        """{id(param): (copy pointer, copy_is_f32)} when every copy matches its parameter right now, else {} --
+        FusedSGD (optim.py) updates the copies in the same pass as the parameters."""
+        if self._plan is None or self._versions is None:
+            return {}
+        if tuple(p._version for p in self._params) != self._versions:
+            return {}
+        return self._shadow
+
+    def mark_synced(self):
+        self._versions = tuple(p._version for p in self._params)
 
     def weight(self, name):
         return self._plan[4][name]
@@ -135,6 +148,12 @@ class StepState:
         self.side = GradSideChannel()
         self.B = self.N = self.nv = self.nm = 0
         self.vis_idx = self.msk_idx = self.slot = self.status = None
+        self.sync = None  # ddp.GradSync when the model is wrapped in bvc_b200.DistributedDataParallel
+
+    def reduce(self, flat):
+        """A stage's parameter gradients (one contiguous buffer) are complete on the stream: start their all-reduce."""
+        if self.sync is not None:
+            self.sync.reduce(flat)
 
 
 def _contig_grad(g):
@@ -169,6 +188,7 @@ class EmbedFn(torch.autograd.Function):
             db = cs
         else:
             L.colsum(dxb, M, D, db)
+        st.reduce(flat)
         return dw, db, None, None, None, None
 
 
@@ -270,6 +290,7 @@ class BlockFn(torch.autograd.Function):
         dxb = _empty((M, d), BF16, dev)
         L.layernorm_bwd(d_u1, x, stats[0], stats[1], ln1w.detach(), dxm, M, d, dx, dxb, g_ln1w, g_ln1b, dxsum=cs_in)
         st.side.put(dx, dxb, cs_in)
+        st.reduce(flat)
 
         gw = g_wqkv.view(3, d, d)
         return (dx, g_ln1w, g_ln1b, gw[0], gw[1], gw[2], g_bqkv[0:d], g_bqkv[2 * d:3 * d], g_wo.view(d, d), g_bo,
@@ -314,6 +335,7 @@ class EncToDecFn(torch.autograd.Function):
         st.side.put(dh, dhb)
         L.gemm(dz, hb, Dd, D, M, a_mn=True, b_mn=True, lda=Dd, ldb=D, out_f32=g_w, k_splits=0)
         L.colsum(dxf, B * nm, Dd, g_tok, ld=Dd, seg=(nm, N, nv))
+        st.reduce(flat)
         return dh, g_w, g_tok.view(1, 1, Dd), None, None, None
 
 
@@ -370,4 +392,5 @@ class HeadLossFn(torch.autograd.Function):
         L.layernorm_bwd(dz, xf, stats[0], stats[1], nw.detach(), None, M, Dd, dxf, dxfb, g_nw, g_nb, ldx=Dd,
                         seg=(nm, N, nv), dxsum=cs)  # visible rows are zero: colsum over the Nm rows == over all rows
         st.side.put(dxf, dxfb, cs)
+        st.reduce(flat)
         return dxf, g_nw, g_nb, g_wh, g_bh, None, None, None, None

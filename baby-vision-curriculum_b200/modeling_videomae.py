@@ -193,6 +193,7 @@ class VideoMAEForPreTraining(nn.Module):
         self.position_embeddings = get_sinusoid_encoding_table(self.num_patches, c.decoder_hidden_size)
         self._pos_dev = {}
         self._cache = Bf16Cache()
+        self._grad_sync = None   # set by bvc_b200.DistributedDataParallel (ddp.py)
         self._nv = None          # cached visible-token count (validated on device every step)
         self._status = None      # device int32 flag: a mask row violated the equal-count contract
         self._strict = os.environ.get("BVC_STRICT_MASK", "0") == "1"
@@ -233,6 +234,13 @@ class VideoMAEForPreTraining(nn.Module):
         ents.append(("e2d", "w", (self.encoder_to_decoder.weight,)))
         ents.append(("head", "w", (self.decoder.head.weight,)))
         return ents
+
+    def weight_shadows(self):
+        """bf16 / packed-bias operand copies of the weights, for an optimizer that refreshes them in its own pass."""
+        return self._cache.shadows()
+
+    def weight_shadows_synced(self):
+        self._cache.mark_synced()
 
     def check_mask_status(self):
         """Synchronise and raise if any forward since the last check saw rows with unequal mask counts."""
@@ -286,6 +294,7 @@ class VideoMAEForPreTraining(nn.Module):
 
             st = StepState(self._cache)
             st.B, st.N, st.nv, st.nm, st.status = B, N, nv, nm, self._status
+            st.sync = self._grad_sync
             st.vis_idx = torch.zeros((B, nv), dtype=torch.int32, device=dev)
             st.msk_idx = torch.zeros((B, nm), dtype=torch.int32, device=dev)
             st.slot = torch.empty((B, N), dtype=torch.int32, device=dev)

@@ -189,9 +189,15 @@ def run_ours(args):
     model = bvc.VideoMAEForPreTraining(bvc.VideoMAEConfig(**c)).to(dev).train()
     xmodel = model
     if world > 1:
-        xmodel = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], output_device=local,
-                                                           find_unused_parameters=False)
-    opt = torch.optim.SGD(xmodel.parameters(), lr=0.1, momentum=0.9, nesterov=True)
+        # the reference's line is DDP(xmodel, device_ids=[rank], output_device=rank, find_unused_parameters=False)
+        # (pretrain_videomae.py:180); bvc.DistributedDataParallel takes the same arguments and all-reduces the engine's
+        # per-stage gradient buffers in place (ddp.py); --ddp torch wraps the same model in torch's DDP instead
+        ddp_cls = bvc.DistributedDataParallel if args.ddp == "bvc" else torch.nn.parallel.DistributedDataParallel
+        xmodel = ddp_cls(model, device_ids=[local], output_device=local, find_unused_parameters=False)
+    if args.optimizer == "fused":  # unscale + SGD-nesterov + bf16 weight copies in one pass
+        opt = bvc.FusedSGD(xmodel.parameters(), lr=0.1, momentum=0.9, nesterov=True, shadow_from=model)
+    else:
+        opt = torch.optim.SGD(xmodel.parameters(), lr=0.1, momentum=0.9, nesterov=True)
     scaler = torch.amp.GradScaler("cuda")
 
     n_pool = 2
@@ -321,8 +327,9 @@ def run_ours(args):
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": f"VideoMAE ViT-{args.config[0].upper()}/16 pretraining step (fwd+loss+bwd+DDP allreduce+"
-                                   f"GradScaler/SGD-nesterov), 16x224x224 clips, tube mask 0.9, batch {B}/GPU",
-                       "global_batch": clips, "parallelism": f"dp{world}", "l2": "inputs larger than L2 "
+                                   f"GradScaler/{'bvc.FusedSGD' if args.optimizer == 'fused' else 'torch.optim.SGD'}-nesterov), 16x224x224 clips, "
+                                   f"tube mask 0.9, batch {B}/GPU",
+                       "global_batch": clips, "parallelism": f"dp{world}" + (f" ({args.ddp} DDP)" if world > 1 else ""), "l2": "inputs larger than L2 "
                        "(616 MB clip batch per step, alternating between two resident batches)"},
             "model_tflops_per_gpu": step_flops / (ms / args.steps) / 1e9,
             "model_tc_frac": step_flops / (ms / args.steps) / 1e9 / peaks["tc"],
@@ -372,6 +379,10 @@ if __name__ == "__main__":
     ap.add_argument("--cpu-batch", type=int, default=4)
     ap.add_argument("--cpu-steps", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--ddp", default="bvc", choices=["bvc", "torch"],
+                    help="N > 1: bvc.DistributedDataParallel (per-stage in-place all-reduce) or torch's DDP")
+    ap.add_argument("--optimizer", default="fused", choices=["fused", "torch"],
+                    help="fused: bvc.FusedSGD (libbvc.so bvc_sgd_step); torch: torch.optim.SGD as in the reference")
     ap.add_argument("--detail", default="", help="write a per-shape kernel time breakdown (JSON) to this path")
     a = ap.parse_args()
     if a.impl == "reference":

@@ -28,7 +28,7 @@ extern "C" {
 #define BVC_ERR_ARG (-1)
 #define BVC_ERR_DRIVER (-2)
 #define BVC_ERR_LAUNCH (-3)
-#define BVC_ABI_VERSION 4
+#define BVC_ABI_VERSION 5
 
 /* library / build info: returns BVC_ABI_VERSION (bumped when a signature changes) */
 int bvc_abi_version(void);
@@ -173,6 +173,22 @@ int bvc_attn_fwd(const void* qkv, int32_t B, int32_t S, int32_t H, float scale, 
                  void* stream);
 int bvc_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, int32_t B, int32_t S,
                  int32_t H, float scale, float* delta, void* dqkv, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * Optimizer step (pretrain_videomae.py:187-197 torch.optim.SGD(nesterov) under GradScaler :312-314) as one
+ * multi-tensor pass.  `table` is a device array of n_entries records (48 bytes each)
+ *   { float* p; float* g; float* m; void* shadow; int64_t n; int32_t shadow_is_f32; int32_t m_uninit; }
+ * per entry, with g' = g / *grad_scale (grad_scale may be null):
+ *   g' += weight_decay * p;  m = m_uninit ? g' : momentum * m + (1 - dampening) * g';
+ *   g'' = nesterov ? g' + momentum * m : m;  p -= lr * g''          (torch/optim/sgd.py _single_tensor_sgd)
+ * g is overwritten by the unscaled gradient when grad_scale is given (what loggingtools.py:107-118 reads after
+ * scaler.step), shadow (bf16, or fp32 when shadow_is_f32) receives the updated parameter (the operand copy the
+ * next forward's GEMMs read), m may be null when momentum == 0.  If found_inf is non-null and *found_inf != 0
+ * the whole call is a no-op (GradScaler's skipped step).
+ * ------------------------------------------------------------------------------------------------------ */
+int bvc_sgd_step(const void* table, int32_t n_entries, float lr, float momentum, float dampening,
+                 float weight_decay, int32_t nesterov, const float* grad_scale, const float* found_inf,
+                 void* stream);
 
 #ifdef __cplusplus
 }

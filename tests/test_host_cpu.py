@@ -105,3 +105,20 @@ def test_bench_flop_model_matches_baseline_md():
     assert abs(bench.flops_per_clip(bench.CONFIGS["base"]) / 1e9 - 202.3) < 0.5
     assert abs(bench.flops_per_clip(bench.CONFIGS["small"]) / 1e9 - 64.0) < 0.5
     assert abs(bench.flops_per_clip(bench.CONFIGS["large"]) / 1e9 - 484.4) < 1.0
+
+
+def test_fused_sgd_host_side():
+    """FusedSGD mirrors torch.optim.SGD's constructor checks and refuses CPU parameters (no CPU fallback)."""
+    import pytest
+    import torch
+    import bvc_b200 as bvc
+    p = torch.nn.Parameter(torch.zeros(8))
+    with pytest.raises(ValueError):
+        bvc.FusedSGD([p], lr=-1.0)
+    with pytest.raises(ValueError):
+        bvc.FusedSGD([p], lr=0.1, nesterov=True)  # nesterov needs momentum (torch/optim/sgd.py)
+    opt = bvc.FusedSGD([p], lr=0.1, momentum=0.9, nesterov=True)
+    assert opt._step_supports_amp_scaling and opt.defaults["nesterov"]
+    p.grad = torch.ones(8)
+    with pytest.raises(bvc.BvcError):
+        opt.step()

@@ -1,0 +1,108 @@
+"""FusedSGD (libbvc.so bvc_sgd_step) against torch.optim.SGD -- the reference's optimizer line
+(pretrain_videomae.py:187-189) -- on identical parameters and gradients, plain and under GradScaler
+(pretrain_videomae.py:312-314), including a skipped (overflow) step.  fp32 arithmetic with the same operation order:
+the tolerance is a few ulp per step (fma contraction vs separate mul + add), 2e-6."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+SHAPES = [(768, 1536), (384,), (3, 5, 7), (1, 1, 384), (2304, 768), (13,)]
+
+
+def _params(seed, dev):
+    g = torch.Generator().manual_seed(seed)
+    return [torch.randn(*s, generator=g).to(dev).requires_grad_(True) for s in SHAPES]
+
+
+def _grads(seed, dev, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return [(torch.randn(*s, generator=g) * scale).to(dev) for s in SHAPES]
+
+
+@pytest.mark.parametrize("kw", [dict(lr=0.1, momentum=0.9, nesterov=True),
+                                dict(lr=0.05, momentum=0.8, dampening=0.1, weight_decay=1e-2),
+                                dict(lr=0.2, weight_decay=5e-4)])
+def test_fused_sgd_matches_torch(kw):
+    import bvc_b200 as bvc
+    dev = torch.device("cuda:0")
+    pa, pb = _params(0, dev), _params(0, dev)
+    oa, ob = torch.optim.SGD(pa, **kw), bvc.FusedSGD(pb, **kw)
+    for step in range(4):
+        for p, q, g in zip(pa, pb, _grads(10 + step, dev)):
+            p.grad, q.grad = g.clone(), g.clone()
+        oa.step()
+        ob.step()
+    torch.cuda.synchronize()
+    for p, q in zip(pa, pb):
+        assert torch.allclose(p, q, rtol=2e-6, atol=2e-6), float((p - q).abs().max())
+    if kw.get("momentum", 0):
+        for p, q in zip(pa, pb):
+            assert torch.allclose(oa.state[p]["momentum_buffer"], ob.state[q]["momentum_buffer"], rtol=2e-6, atol=2e-6)
+    assert all(q._version > 0 for q in pb)  # autograd is told about the in-place update
+    if kw.get("momentum", 0):  # same per-parameter state keys as torch.optim.SGD (checkpoints interchange)
+        assert set(ob.state_dict()["state"][0]) == set(oa.state_dict()["state"][0])
+
+
+def test_fused_sgd_under_gradscaler_with_overflow_skip():
+    import bvc_b200 as bvc
+    dev = torch.device("cuda:0")
+    kw = dict(lr=0.1, momentum=0.9, nesterov=True)
+    pa, pb = _params(1, dev), _params(1, dev)
+    oa, ob = torch.optim.SGD(pa, **kw), bvc.FusedSGD(pb, **kw)
+    sa, sb = torch.amp.GradScaler("cuda", init_scale=1024.0), torch.amp.GradScaler("cuda", init_scale=1024.0)
+    for step in range(5):
+        gs = _grads(20 + step, dev, scale=float(sa.get_scale()))
+        if step in (0, 2):  # overflow on the very first step (momentum still uninitialised) and later
+            gs[1][3] = float("inf")
+        for p, q, g in zip(pa, pb, gs):
+            p.grad, q.grad = g.clone(), g.clone()
+        # the scaler's bookkeeping normally starts in scale(); emulate it
+        sa.scale(torch.ones((), device=dev))
+        sb.scale(torch.ones((), device=dev))
+        sa.step(oa)
+        sb.step(ob)
+        if step not in (0, 2):  # .grad holds the UNSCALED gradient after step (loggingtools.py:107-118 reads it)
+            for p, q in zip(pa, pb):
+                assert torch.allclose(p.grad, q.grad, rtol=2e-6, atol=2e-6)
+        sa.update()
+        sb.update()
+        assert sa.get_scale() == sb.get_scale()
+    torch.cuda.synchronize()
+    for p, q in zip(pa, pb):
+        assert torch.isfinite(q).all()
+        assert torch.allclose(p, q, rtol=2e-6, atol=2e-6), float((p - q).abs().max())
+
+
+def test_fused_sgd_refreshes_weight_copies():
+    """shadow_from=model: the bf16 operand copies are rewritten by the optimizer pass, so a second forward after the
+    step gives the same loss as a model whose copies were re-cast from scratch."""
+    import numpy as np
+    import bvc_b200 as bvc
+    from oracle import videomae_oracle as O
+    from tests.helpers import bvc_config
+    dev = torch.device("cuda:0")
+    cfg = O.make_config("tiny")
+    params = O.init_params(cfg, seed=1, perturb=True)
+    x = O.synthetic_clip(2, cfg, seed=2, image_like=True).to(dev)
+    np.random.seed(3)
+    mask = O.batch_tube_masks(2, cfg.grid, 0.5).to(dev)
+    losses = []
+    for fused in (False, True):
+        model = bvc.VideoMAEForPreTraining(bvc_config(cfg))
+        model.load_state_dict(params, strict=True)
+        model = model.to(dev).train()
+        opt = (bvc.FusedSGD(model.parameters(), lr=0.05, momentum=0.9, nesterov=True, shadow_from=model) if fused
+               else torch.optim.SGD(model.parameters(), lr=0.05, momentum=0.9, nesterov=True))
+        seq = []
+        for _ in range(3):
+            opt.zero_grad()
+            loss = model(x, bool_masked_pos=mask).loss
+            loss.backward()
+            opt.step()
+            seq.append(float(loss))
+        losses.append(seq)
+    assert opt.table_builds <= 3  # stable pointers in the real loop: first step, second step (momentum flags), cached
+    assert losses[0][1] < losses[0][0]
+    for a, b in zip(*losses):
+        assert abs(a - b) <= 2e-5 * abs(a), losses

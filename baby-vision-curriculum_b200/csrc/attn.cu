@@ -24,6 +24,21 @@
 
 namespace bvc {
 
+// -DBVC_TRACE (tools/gpu_attn_trace.py builds a separate libbvc_trace.so): per-phase SM clock stamps of CTA 0's
+// backward pipeline, read back through bvc_debug_trace_copy.  Not compiled into libbvc.so.
+#ifdef BVC_TRACE
+constexpr int kTraceRoles = 3, kTraceTiles = 256, kTracePoints = 8;
+__device__ long long g_trace[kTraceRoles * kTraceTiles * kTracePoints];
+#define BVC_TR(role, g, pt)                                                                              \
+  do {                                                                                                   \
+    if (blockIdx.x == 0 && (g) < kTraceTiles) g_trace[((role) * kTraceTiles + (g)) * kTracePoints + (pt)] = clock64(); \
+  } while (0)
+#else
+#define BVC_TR(role, g, pt) \
+  do {                      \
+  } while (0)
+#endif
+
 constexpr int kTile = 128;          // rows per Q / KV tile
 constexpr int kTileBytes = 16384;   // 128 x 64 bf16
 constexpr float kLog2e = 1.4426950408889634f;
@@ -394,45 +409,64 @@ __global__ void __launch_bounds__(256) attn_delta_kernel(const bf16* __restrict_
 // (setmaxnreg): the compute threads hold a 64-wide slice of S and dP plus their packed P / dS outputs in registers.
 constexpr int kBwdThreads = 384;
 constexpr int kBwdRegsCtl = 88, kBwdRegsCompute = 208;
-// resident pair (2 tiles) + stream ring (4 stages x 2 tiles: the streamed tiles' TMA latency was the critical path
-// with 2 stages -- ncu: 30 % of the compute warps' samples waiting for S/dP) + per-column statistics ring + barriers.
+// PERSISTENT: one CTA per SM walks a list of work items (owned tile, head, clip).  Everything is pipelined ACROSS
+// items through the same barriers that pipeline the tiles of one item -- the TMA warp runs ahead into the next item's
+// resident and streamed tiles, the MMA warp issues the next item's first S / dP while the compute warps store the
+// previous item's accumulators -- so the per-CTA costs of the one-CTA-per-item version (launch, barrier init, TMEM
+// allocation, the DRAM latency of the first tiles, the epilogue; ~8.7k clk per item, measured: 25 % of an S = 1568 item
+// and 80 % of an S = 160 item) are paid once per SM or hidden.
+// smem: resident pair x 2 buffers + stream ring (4 stages x 2 tiles) + one "augmentation" tile + barriers.
 // P / dS never touch shared memory: they go back into TMEM (packed bf16) as the A operands of the accumulating MMAs.
-// With P / dS staged in shared memory the kernel was bound by the shared-memory port (per 128x128 tile pair: 160 KB of
-// UMMA operand reads + 64 KB st.shared + 32 KB TMA fill = 2048 clk at 128 B/clk against 1024 clk of tensor work).
+//
+// MODE_KV works on the transposed tile, where the softmax statistics (lse, delta) vary along the COLUMNS a thread
+// holds.  Fetching them per column (staged in shared memory, one barrier per tile) doubled the math phase (trace:
+// 2021 clk vs 1041 without), so the subtraction is folded into the score MMAs instead: one extra K = 16 step with
+//   A = [1 1 1 0 ...]  (rows = keys)      B = three-way bf16 split of -lse/scale (resp. -delta)  (rows = queries)
+// makes the tensor core deliver S - lse/scale and dP - delta directly (the split carries 24 mantissa bits, the
+// products with 1.0 are exact, accumulation is fp32).  The three [128][16] operands live in k-steps 0 / 1 / 2 of one
+// 128B-swizzled [128][64] tile; the compute warps rewrite the two statistic columns once per streamed tile.
 constexpr int kBwdStages = 4;
-constexpr int kBwdStatBytes = 2 * 2 * kTile * 4;  // [2 buffers][nl2 | nds][128] fp32
-constexpr int kBwdSmem = kTileBytes * (2 + 2 * kBwdStages) + kBwdStatBytes + 256;
+constexpr int kBwdSmem = kTileBytes * (4 + 2 * kBwdStages + 1) + 256;
 
 template <int MODE_KV>
 __global__ void __launch_bounds__(kBwdThreads, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
-                const float* __restrict__ lse, const float* __restrict__ delta, bf16* __restrict__ dqkv, int S, int H,
-                float scale) {
+                const __grid_constant__ CUtensorMap tm_dqkv, const float* __restrict__ lse,
+                const float* __restrict__ delta, int S, int H, int n_work, float scale) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* sR0 = smem;                     // MODE_KV: K_j    | MODE_Q: Q_i
-  uint8_t* sR1 = smem + kTileBytes;        // MODE_KV: V_j    | MODE_Q: dO_i
-  uint8_t* sX = smem + 2 * kTileBytes;                     // [stages] MODE_KV: Q_i  | MODE_Q: K_j
-  uint8_t* sY = smem + (2 + kBwdStages) * kTileBytes;      // [stages] MODE_KV: dO_i | MODE_Q: V_j
-  float* sStat = reinterpret_cast<float*>(smem + (2 + 2 * kBwdStages) * kTileBytes);  // MODE_KV only
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (2 + 2 * kBwdStages) * kTileBytes + kBwdStatBytes);
-  uint64_t* r_full = bars + 0;
-  uint64_t* st_full = bars + 1;                  // [stages]
-  uint64_t* st_empty = bars + 1 + kBwdStages;    // [stages]
-  uint64_t* sdp_full = bars + 1 + 2 * kBwdStages;
+  uint8_t* sR = smem;                                      // [2 buffers][R0 | R1]; MODE_KV: K_j, V_j | MODE_Q: Q_i, dO_i
+  uint8_t* sX = smem + 4 * kTileBytes;                     // [stages] MODE_KV: Q_i  | MODE_Q: K_j
+  uint8_t* sY = smem + (4 + kBwdStages) * kTileBytes;      // [stages] MODE_KV: dO_i | MODE_Q: V_j
+  uint8_t* sAug = smem + (4 + 2 * kBwdStages) * kTileBytes;  // MODE_KV: ones | -lse/scale | -delta (k-steps 0, 1, 2)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (5 + 2 * kBwdStages) * kTileBytes);
+  uint64_t* r_full = bars + 0;                   // [2]
+  uint64_t* r_empty = bars + 2;                  // [2]
+  uint64_t* st_full = bars + 4;                  // [stages]
+  uint64_t* st_empty = bars + 4 + kBwdStages;    // [stages]
+  uint64_t* sdp_full = bars + 4 + 2 * kBwdStages;
   uint64_t* sdp_free = sdp_full + 1;
   uint64_t* pds_full = sdp_full + 2;
   uint64_t* pds_free = sdp_full + 3;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sdp_full + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int own0 = blockIdx.x * kTile, h = blockIdx.y, b = blockIdx.z;
-  const int n_it = (S + kTile - 1) / kTile;
+  const int n_it = (S + kTile - 1) / kTile;  // tiles per sequence = owned tiles per (clip, head) = streamed tiles per item
+  // work item w -> (owned tile, head, clip), owned tile fastest: the CTAs running at any moment share a few (clip,
+  // head) pairs, so the streamed tiles are served from L2
+  const int n_my = (n_work - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int n_glob = n_my * n_it;            // streamed tiles this CTA processes, over all its items
+  auto item_tile = [&](int k) { return ((int)blockIdx.x + k * (int)gridDim.x) % n_it; };
+  auto item_bh = [&](int k) { return ((int)blockIdx.x + k * (int)gridDim.x) / n_it; };  // = b * H + h
 
   if (threadIdx.x == 0) {
     if ((smem_u32(smem) & 1023u) != 0) __trap();
     tma_prefetch_desc(&tm_qkv);
     tma_prefetch_desc(&tm_do);
-    mbar_init(r_full, 1);
+    tma_prefetch_desc(&tm_dqkv);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&r_full[i], 1);
+      mbar_init(&r_empty[i], 1);
+    }
     for (int i = 0; i < kBwdStages; ++i) {
       mbar_init(&st_full[i], 1);
       mbar_init(&st_empty[i], 1);
@@ -454,111 +488,145 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
 
   if (warp < 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kBwdRegsCtl));
-  if (warp == 0) {
-    if (lane == 0) {
-      mbar_expect_tx(r_full, 2 * kTileBytes);
-      if (MODE_KV) {
-        tma_load_4d(sR0, &tm_qkv, r_full, 0, H + h, own0, b);
-        tma_load_4d(sR1, &tm_qkv, r_full, 0, 2 * H + h, own0, b);
-      } else {
-        tma_load_4d(sR0, &tm_qkv, r_full, 0, h, own0, b);
-        tma_load_4d(sR1, &tm_do, r_full, 0, h, own0, b);
-      }
-      for (int i = 0; i < n_it; ++i) {
-        const int st = i % kBwdStages;
-        mbar_wait(&st_empty[st], ((uint32_t)(i / kBwdStages) & 1u) ^ 1u);
-        mbar_expect_tx(&st_full[st], 2 * kTileBytes);
-        if (MODE_KV) {
-          tma_load_4d(sX + st * kTileBytes, &tm_qkv, &st_full[st], 0, h, i * kTile, b);
-          tma_load_4d(sY + st * kTileBytes, &tm_do, &st_full[st], 0, h, i * kTile, b);
-        } else {
-          tma_load_4d(sX + st * kTileBytes, &tm_qkv, &st_full[st], 0, H + h, i * kTile, b);
-          tma_load_4d(sY + st * kTileBytes, &tm_qkv, &st_full[st], 0, 2 * H + h, i * kTile, b);
+    if (warp == 0) {
+      if (lane == 0) {
+        int g = 0;
+        for (int k = 0; k < n_my; ++k) {
+          const int own0 = item_tile(k) * kTile, bh = item_bh(k), h = bh % H, b = bh / H;
+          uint8_t* r0 = sR + (k & 1) * 2 * kTileBytes;
+          mbar_wait(&r_empty[k & 1], ((uint32_t)(k >> 1) & 1u) ^ 1u);
+          mbar_expect_tx(&r_full[k & 1], 2 * kTileBytes);
+          if (MODE_KV) {
+            tma_load_4d(r0, &tm_qkv, &r_full[k & 1], 0, H + h, own0, b);
+            tma_load_4d(r0 + kTileBytes, &tm_qkv, &r_full[k & 1], 0, 2 * H + h, own0, b);
+          } else {
+            tma_load_4d(r0, &tm_qkv, &r_full[k & 1], 0, h, own0, b);
+            tma_load_4d(r0 + kTileBytes, &tm_do, &r_full[k & 1], 0, h, own0, b);
+          }
+          for (int i = 0; i < n_it; ++i, ++g) {
+            const int st = g % kBwdStages;
+            mbar_wait(&st_empty[st], ((uint32_t)(g / kBwdStages) & 1u) ^ 1u);
+            mbar_expect_tx(&st_full[st], 2 * kTileBytes);
+            if (MODE_KV) {
+              tma_load_4d(sX + st * kTileBytes, &tm_qkv, &st_full[st], 0, h, i * kTile, b);
+              tma_load_4d(sY + st * kTileBytes, &tm_do, &st_full[st], 0, h, i * kTile, b);
+            } else {
+              tma_load_4d(sX + st * kTileBytes, &tm_qkv, &st_full[st], 0, H + h, i * kTile, b);
+              tma_load_4d(sY + st * kTileBytes, &tm_qkv, &st_full[st], 0, 2 * H + h, i * kTile, b);
+            }
+          }
         }
       }
-    }
-  } else if (warp == 1) {
-    // MMA issuer: the whole warp walks the (uniform) control flow and polls the barriers, one elected lane issues
-    constexpr uint32_t idesc_acc = umma_idesc_bf16(64, 0, 1, 128);  // A from TMEM (K-major), B MN-major, N = 64
-    // k = 0 descriptors; a K = 16 step moves the start address by 32 B (K-major, +2 in the descriptor's 16-byte
-    // units) or by 16 rows = 2048 B (MN-major, +128)
-    const uint64_t dR0 = desc_k(smem_u32(sR0), 0), dR1 = desc_k(smem_u32(sR1), 0);
-    // ragged last tile of the STREAMED operand: it is the N of the score MMAs in both modes (MODE_KV streams the
-    // query tiles and computes S^T = K Q^T; MODE_Q streams the K/V tiles and computes S = Q K^T) and the reduction
-    // dimension of the accumulating MMAs, so both shrink to its valid rows rounded up to 16
-    auto valid16 = [&](int t0) { return min(kTile, (S - t0 + 15) & ~15); };
-    auto issue_s_dp = [&](int st, int it) {
-      const uint32_t idesc_s = umma_idesc_bf16(valid16(it * kTile), 0, 0, 128);
-      const uint64_t dX = desc_k(smem_u32(sX + st * kTileBytes), 0), dY = desc_k(smem_u32(sY + st * kTileBytes), 0);
-      // MODE_KV: S^T = K Q^T, dP^T = V dO^T (rows = kv, cols = q);  MODE_Q: S = Q K^T, dP = dO V^T (rows = q)
+    } else if (warp == 1) {
+      // MMA issuer: the whole warp walks the (uniform) control flow and polls the barriers, one elected lane issues.
+      // One flat loop over the CTA's streamed tiles g (item k = g / n_it, tile i = g % n_it): S / dP of tile g + 1 --
+      // possibly the next item's first tile -- is issued before the accumulating MMAs of tile g.
+      constexpr uint32_t idesc_acc = umma_idesc_bf16(64, 0, 1, 128);  // A from TMEM (K-major), B MN-major, N = 64
+      // ragged last tile of the STREAMED operand: it is the N of the score MMAs in both modes (MODE_KV streams the
+      // query tiles and computes S^T = K Q^T; MODE_Q streams the K/V tiles and computes S = Q K^T) and the reduction
+      // dimension of the accumulating MMAs, so both shrink to its valid rows rounded up to 16
+      auto valid16 = [&](int i) { return min(kTile, (S - i * kTile + 15) & ~15); };
+      // k = 0 descriptors; a K = 16 step moves the start address by 32 B (K-major, +2 in the descriptor's 16-byte
+      // units) or by 16 rows = 2048 B (MN-major, +128)
+      const uint64_t dAug = desc_k(smem_u32(sAug), 0);
+      auto issue_s_dp = [&](int k, int i, int st) {
+        const uint32_t idesc_s = umma_idesc_bf16(valid16(i), 0, 0, 128);
+        const uint32_t aR = smem_u32(sR + (k & 1) * 2 * kTileBytes);
+        const uint64_t dR0 = desc_k(aR, 0), dR1 = desc_k(aR + kTileBytes, 0);
+        const uint64_t dX = desc_k(smem_u32(sX + st * kTileBytes), 0), dY = desc_k(smem_u32(sY + st * kTileBytes), 0);
+        // MODE_KV: S^T = K Q^T, dP^T = V dO^T (rows = kv, cols = q);  MODE_Q: S = Q K^T, dP = dO V^T (rows = q)
 #pragma unroll
-      for (int k = 0; k < 4; ++k) umma_bf16_ss(tS, dR0 + 2 * k, dX + 2 * k, idesc_s, k > 0);
+        for (int kk = 0; kk < 4; ++kk) umma_bf16_ss(tS, dR0 + 2 * kk, dX + 2 * kk, idesc_s, kk > 0);
+        if (MODE_KV) umma_bf16_ss(tS, dAug, dAug + 2, idesc_s, 1);       // S^T - lse_q / scale
 #pragma unroll
-      for (int k = 0; k < 4; ++k) umma_bf16_ss(tDP, dR1 + 2 * k, dY + 2 * k, idesc_s, k > 0);
-    };
-    mbar_wait(r_full, 0);
-    mbar_wait(&st_full[0], 0);
-    tc_fence_after();
-    if (elect_one()) {
-      issue_s_dp(0, 0);
-      umma_commit(sdp_full);
-    }
-    __syncwarp();
-    for (int i = 0; i < n_it; ++i) {
-      if (i + 1 < n_it) {
-        const int st = (i + 1) % kBwdStages;
-        mbar_wait(&st_full[st], (uint32_t)((i + 1) / kBwdStages) & 1u);
-        mbar_wait(sdp_free, (uint32_t)i & 1u);
+        for (int kk = 0; kk < 4; ++kk) umma_bf16_ss(tDP, dR1 + 2 * kk, dY + 2 * kk, idesc_s, kk > 0);
+        if (MODE_KV) umma_bf16_ss(tDP, dAug, dAug + 4, idesc_s, 1);      // dP^T - delta_q
+      };
+      // the compute warps have written the augmentation tile (ones + tile 0's statistics)
+      if (MODE_KV) asm volatile("bar.sync 2, 288;" ::: "memory");
+      if (n_glob > 0) {
+        mbar_wait(&r_full[0], 0);
+        mbar_wait(&st_full[0], 0);
         tc_fence_after();
         if (elect_one()) {
-          issue_s_dp(st, i + 1);
+          issue_s_dp(0, 0, 0);
           umma_commit(sdp_full);
         }
         __syncwarp();
       }
-      mbar_wait(pds_full, (uint32_t)i & 1u);
-      tc_fence_after();
-      const int cst = i % kBwdStages;
-      const int ksteps = valid16(i * kTile) >> 4;  // streamed tile = the reduction dimension in both modes
-      if (elect_one()) {
-        const uint64_t dX = desc_mn(smem_u32(sX + cst * kTileBytes), 0, 8192);
-        const uint64_t dY = desc_mn(smem_u32(sY + cst * kTileBytes), 0, 8192);
-        const uint32_t acc0 = i > 0;
-        if (MODE_KV) {
-          // dV[kv, d] += P^T dO : A = P^T (TMEM, m = kv, k = q), B = dO_i (MN-major: n = d, k = q)
-          // dK[kv, d] += dS^T Q : A = dS^T (TMEM), B = Q_i (MN-major)
-          if (ksteps == 8) {
-#pragma unroll
-            for (int k = 0; k < 8; ++k) umma_bf16_ts(tA0, tP + k * 8, dY + 128 * k, idesc_acc, acc0 | (k > 0));
-#pragma unroll
-            for (int k = 0; k < 8; ++k) umma_bf16_ts(tA1, tDS + k * 8, dX + 128 * k, idesc_acc, acc0 | (k > 0));
-          } else {
-            for (int k = 0; k < ksteps; ++k) umma_bf16_ts(tA0, tP + k * 8, dY + 128 * k, idesc_acc, acc0 | (k > 0));
-            for (int k = 0; k < ksteps; ++k) umma_bf16_ts(tA1, tDS + k * 8, dX + 128 * k, idesc_acc, acc0 | (k > 0));
-          }
-        } else {
-          // dQ[q, d] += dS K : A = dS (TMEM, m = q, k = kv), B = K_j (MN-major: n = d, k = kv)
-          if (ksteps == 8) {
-#pragma unroll
-            for (int k = 0; k < 8; ++k) umma_bf16_ts(tA0, tDS + k * 8, dX + 128 * k, idesc_acc, acc0 | (k > 0));
-          } else {
-            for (int k = 0; k < ksteps; ++k) umma_bf16_ts(tA0, tDS + k * 8, dX + 128 * k, idesc_acc, acc0 | (k > 0));
-          }
+      int k = 0, i = 0;  // item / tile of g
+      for (int g = 0; g < n_glob; ++g) {
+        int k1 = k, i1 = i + 1;  // item / tile of g + 1
+        if (i1 == n_it) {
+          i1 = 0;
+          ++k1;
         }
-        umma_commit(pds_free);
-        umma_commit(&st_empty[cst]);
+        if (lane == 0) BVC_TR(2, g, 0);
+        if (g + 1 < n_glob) {
+          const int st1 = (g + 1) % kBwdStages;
+          if (i1 == 0) mbar_wait(&r_full[k1 & 1], (uint32_t)(k1 >> 1) & 1u);
+          mbar_wait(&st_full[st1], (uint32_t)((g + 1) / kBwdStages) & 1u);
+          if (lane == 0) BVC_TR(2, g, 1);
+          mbar_wait(sdp_free, (uint32_t)g & 1u);
+          if (lane == 0) BVC_TR(2, g, 2);
+          tc_fence_after();
+          if (elect_one()) {
+            issue_s_dp(k1, i1, st1);
+            umma_commit(sdp_full);
+          }
+          __syncwarp();
+        }
+        if (lane == 0) BVC_TR(2, g, 3);
+        mbar_wait(pds_full, (uint32_t)g & 1u);
+        if (lane == 0) BVC_TR(2, g, 4);
+        tc_fence_after();
+        const int cst = g % kBwdStages;
+        const int ksteps = valid16(i) >> 4;  // streamed tile = the reduction dimension in both modes
+        if (elect_one()) {
+          const uint64_t dX = desc_mn(smem_u32(sX + cst * kTileBytes), 0, 8192);
+          const uint64_t dY = desc_mn(smem_u32(sY + cst * kTileBytes), 0, 8192);
+          const uint32_t acc0 = i > 0;
+          if (MODE_KV) {
+            // dV[kv, d] += P^T dO : A = P^T (TMEM, m = kv, k = q), B = dO_i (MN-major: n = d, k = q)
+            // dK[kv, d] += dS^T Q : A = dS^T (TMEM), B = Q_i (MN-major)
+            if (ksteps == 8) {
+#pragma unroll
+              for (int kk = 0; kk < 8; ++kk) umma_bf16_ts(tA0, tP + kk * 8, dY + 128 * kk, idesc_acc, acc0 | (kk > 0));
+#pragma unroll
+              for (int kk = 0; kk < 8; ++kk) umma_bf16_ts(tA1, tDS + kk * 8, dX + 128 * kk, idesc_acc, acc0 | (kk > 0));
+            } else {
+              for (int kk = 0; kk < ksteps; ++kk)
+                umma_bf16_ts(tA0, tP + kk * 8, dY + 128 * kk, idesc_acc, acc0 | (kk > 0));
+              for (int kk = 0; kk < ksteps; ++kk)
+                umma_bf16_ts(tA1, tDS + kk * 8, dX + 128 * kk, idesc_acc, acc0 | (kk > 0));
+            }
+          } else {
+            // dQ[q, d] += dS K : A = dS (TMEM, m = q, k = kv), B = K_j (MN-major: n = d, k = kv)
+            if (ksteps == 8) {
+#pragma unroll
+              for (int kk = 0; kk < 8; ++kk) umma_bf16_ts(tA0, tDS + kk * 8, dX + 128 * kk, idesc_acc, acc0 | (kk > 0));
+            } else {
+              for (int kk = 0; kk < ksteps; ++kk)
+                umma_bf16_ts(tA0, tDS + kk * 8, dX + 128 * kk, idesc_acc, acc0 | (kk > 0));
+            }
+          }
+          umma_commit(pds_free);
+          umma_commit(&st_empty[cst]);
+        }
+        __syncwarp();
+        if (lane == 0) BVC_TR(2, g, 5);
+        k = k1;
+        i = i1;
       }
-      __syncwarp();
     }
-  }
   } else {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kBwdRegsCompute));
     // 8 compute warps: TMEM lane quadrant q4 = warp % 4 (rows q4*32 .. +31 of the score tile), column half = (warp-4)/4.
     // MODE_Q : row = query, columns = keys;   statistics (lse, delta) are per ROW: two registers per thread.
-    // MODE_KV: row = key,   columns = queries; statistics are per COLUMN: staged in shared memory per streamed tile.
+    // MODE_KV: row = key,   columns = queries; the statistics were subtracted by the augmented score MMAs.
     // No masking anywhere: rows / columns past the end of the sequence meet zero-filled operand rows in every MMA
-    // that consumes them (or land in accumulator rows that are never stored); they only have to stay finite, which
-    // the clamped statistics loads guarantee.
+    // that consumes them (or land in accumulator rows that the TMA store clips); they only have to stay finite,
+    // which the clamped statistics loads guarantee.
     const int e = warp - 4;
     const int q4 = warp & 3;
     const int half = e >> 2;
@@ -566,118 +634,176 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
     const int ct = threadIdx.x - 128;  // 0..255
     const uint32_t lane_base = (uint32_t)(q4 * 32) << 16;
     const float c_log2 = scale * kLog2e;
-    const float* lse_bh = lse + ((long long)b * H + h) * S;
-    const float* dl_bh = delta + ((long long)b * H + h) * S;
     const uint64_t cl2 = pack2(c_log2, c_log2), sc2 = pack2(scale, scale);
-    // MODE_KV: compute thread ct stages statistic (ct < 128 ? -lse*log2e : -delta*scale) of query ct % 128
-    auto load_stat = [&](int it) {
-      const int qg = min(it * kTile + (ct & 127), S - 1);
-      return __ldg((ct < 128 ? lse_bh : dl_bh) + qg);
+    // MODE_KV: compute thread ct owns statistic (ct < 128 ? lse : delta) of query ct % 128 of every streamed tile and
+    // writes its three-way bf16 split into row ct % 128 of the augmentation tile (k-step 1 resp. 2 = 16-byte chunk
+    // 2 resp. 4 of the 128B-swizzled row; the second chunk of each k-step stays zero)
+    const int arow = ct & 127;
+    uint8_t* aug_dst = sAug + arow * 128 + ((((ct < 128) ? 2 : 4) ^ (arow & 7)) << 4);
+    auto load_stat = [&](int kk, int ii) {
+      const int qg = min(ii * kTile + arow, S - 1);
+      return __ldg((ct < 128 ? lse : delta) + (long long)item_bh(kk) * S + qg);
     };
-    auto put_stat = [&](int it, float v) { sStat[(it & 1) * 2 * kTile + ct] = ct < 128 ? -v * kLog2e : -v * scale; };
-    float st_next = 0.f;
-    uint64_t nl2 = 0, nd2 = 0;
-    if (MODE_KV) {
-      put_stat(0, load_stat(0));
-      if (n_it > 1) st_next = load_stat(1);
-    } else {
-      const int qc = min(own0 + row, S - 1);
-      const float l = -__ldg(lse_bh + qc) * kLog2e, d = -__ldg(dl_bh + qc) * scale;
-      nl2 = pack2(l, l);
-      nd2 = pack2(d, d);
-    }
-    for (int i = 0; i < n_it; ++i) {
-      mbar_wait(sdp_full, (uint32_t)i & 1u);
-      tc_fence_after();
-      uint32_t sv[2][32], dv[2][32];
-#pragma unroll
-      for (int c = 0; c < 2; ++c) tmem_ld_32x32b_x32(tS + lane_base + half * 64 + c * 32, sv[c]);
-#pragma unroll
-      for (int c = 0; c < 2; ++c) tmem_ld_32x32b_x32(tDP + lane_base + half * 64 + c * 32, dv[c]);
-      // all four loads landed before the TMEM columns are handed back (the math below must not be hoisted between
-      // the loads: that delays sdp_free, and with it the next tile's S / dP MMAs, by half a tile of MUFU work)
-      tmem_ld_wait_pin(sv[0]);
-      tmem_ld_wait_pin(sv[1]);
-      tmem_ld_wait_pin(dv[0]);
-      tmem_ld_wait_pin(dv[1]);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(sdp_free);
-      if (MODE_KV) {
-        // every compute warp is past tile i-1's math (which read buffer (i+1)&1) and tile i's statistics are visible
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        if (i + 1 < n_it) {
-          put_stat(i + 1, st_next);
-          if (i + 2 < n_it) st_next = load_stat(i + 2);
-        }
+    auto put_aug = [&](float v) {
+      v = ct < 128 ? -v / scale : -v;
+      const float hi = __bfloat162float(__float2bfloat16_rn(v));
+      const float r1 = v - hi;
+      const float mid = __bfloat162float(__float2bfloat16_rn(r1));
+      const float lo = r1 - mid;
+      *reinterpret_cast<uint4*>(aug_dst) = make_uint4(pack_bf16x2(hi, mid), pack_bf16x2(lo, 0.f), 0u, 0u);
+    };
+    // MODE_Q: this thread's row statistics of item kk
+    auto load_row = [&](int kk, float& l, float& d) {
+      const int qc = min(item_tile(kk) * kTile + row, S - 1);
+      const long long o = (long long)item_bh(kk) * S + qc;
+      l = __ldg(lse + o);
+      d = __ldg(delta + o);
+    };
+    float st_next = 0.f, l_cur = 0.f, d_cur = 0.f;
+    int sk = 0, si = 0;  // (item, tile) whose statistic st_next holds: always the tile after the one being computed
+    auto stat_advance = [&]() {
+      if (++si == n_it) {
+        si = 0;
+        ++sk;
       }
-      const float* st_l = sStat + (i & 1) * 2 * kTile + half * 64;
-      const float* st_d = st_l + kTile;
-      // this thread's 64 P / dS values of the tile, packed bf16x2; the math overlaps the previous tile's accumulating
-      // MMAs, which are still reading the TMEM P / dS operands
-      uint32_t pk[32], dk[32];
+    };
+    if (MODE_KV) {
+      if (ct < 128) {  // constant part of the augmentation tile: ones in k-step 0, zeros in every other static chunk
+        const uint4 ones = make_uint4(pack_bf16x2(1.f, 1.f), pack_bf16x2(1.f, 0.f), 0u, 0u);
+        const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
-      for (int c = 0; c < 2; ++c)
+        for (int c = 0; c < 8; ++c)
+          if (c != 2 && c != 4) *reinterpret_cast<uint4*>(sAug + arow * 128 + ((c ^ (arow & 7)) << 4)) = c == 0 ? ones : zero;
+      }
+      if (n_glob > 0) {
+        put_aug(load_stat(0, 0));
+        stat_advance();
+        if (n_glob > 1) st_next = load_stat(sk, si);
+      }
+      fence_async_smem();
+      asm volatile("bar.sync 2, 288;" ::: "memory");  // with the MMA warp, once
+    } else if (n_glob > 0) {
+      load_row(0, l_cur, d_cur);
+    }
+    int g = 0;
+    for (int k = 0; k < n_my; ++k) {
+      const int own0 = item_tile(k) * kTile, bh = item_bh(k), h = bh % H, b = bh / H;
+      uint64_t nl2 = 0, nd2 = 0;
+      float l_nxt = 0.f, d_nxt = 0.f;
+      if (!MODE_KV) {
+        const float l = -l_cur * kLog2e, d = -d_cur * scale;
+        nl2 = pack2(l, l);
+        nd2 = pack2(d, d);
+        if (k + 1 < n_my) load_row(k + 1, l_nxt, d_nxt);  // in flight during this whole item
+      }
+      for (int i = 0; i < n_it; ++i, ++g) {
+        const bool tr = lane == 0 && q4 == 0;
+        if (tr) BVC_TR(half, g, 0);
+        mbar_wait(sdp_full, (uint32_t)g & 1u);
+        if (tr) BVC_TR(half, g, 1);
+        tc_fence_after();
+        if (MODE_KV && g + 1 < n_glob) {
+          // tile g's score MMAs are done reading the statistic columns: write tile g+1's (read by the S / dP MMAs
+          // that the MMA warp issues once this warp has arrived on sdp_free below)
+          put_aug(st_next);
+          fence_async_smem();
+          stat_advance();
+          if (g + 2 < n_glob) st_next = load_stat(sk, si);  // in flight during this tile's math
+        }
+        uint32_t sv[2][32], dv[2][32];
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
+        for (int c = 0; c < 2; ++c) tmem_ld_32x32b_x32(tS + lane_base + half * 64 + c * 32, sv[c]);
 #pragma unroll
-          for (int t = 0; t < 8; t += 2) {
-            const int j = g * 8 + t;
-            // per-column statistics: one 8-byte broadcast load yields the packed pair directly
-            const uint64_t nlp = MODE_KV ? *reinterpret_cast<const uint64_t*>(st_l + c * 32 + j) : nl2;
-            const uint64_t ndp = MODE_KV ? *reinterpret_cast<const uint64_t*>(st_d + c * 32 + j) : nd2;
-            // P = exp2(S * scale * log2e - lse * log2e)
-            const uint64_t x2 = ffma2(pack2(__uint_as_float(sv[c][j]), __uint_as_float(sv[c][j + 1])), cl2, nlp);
+        for (int c = 0; c < 2; ++c) tmem_ld_32x32b_x32(tDP + lane_base + half * 64 + c * 32, dv[c]);
+        // all four loads landed before the TMEM columns are handed back (the math below must not be hoisted between
+        // the loads: that delays sdp_free, and with it the next tile's S / dP MMAs, by half a tile of MUFU work)
+        tmem_ld_wait_pin(sv[0]);
+        tmem_ld_wait_pin(sv[1]);
+        tmem_ld_wait_pin(dv[0]);
+        tmem_ld_wait_pin(dv[1]);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(sdp_free);
+        if (tr) BVC_TR(half, g, 2);
+        // this thread's 64 P / dS values of the tile, packed bf16x2; the math overlaps the previous tile's
+        // accumulating MMAs, which are still reading the TMEM P / dS operands
+        uint32_t pk[32], dk[32];
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            const uint64_t s2 = pack2(__uint_as_float(sv[c][j]), __uint_as_float(sv[c][j + 1]));
+            const uint64_t p2 = pack2(__uint_as_float(dv[c][j]), __uint_as_float(dv[c][j + 1]));
+            // P = exp2((S - lse/scale) * scale * log2e);  dS = P * (dP - delta) * scale
+            const uint64_t x2 = MODE_KV ? fmul2(s2, cl2) : ffma2(s2, cl2, nl2);
+            const uint64_t y2 = MODE_KV ? fmul2(p2, sc2) : ffma2(p2, sc2, nd2);
             float a0, a1;
             unpack2(x2, a0, a1);
             const float p0 = exp2f(a0), p1 = exp2f(a1);
-            // dS = P * (dP - delta) * scale
-            const uint64_t y2 = ffma2(pack2(__uint_as_float(dv[c][j]), __uint_as_float(dv[c][j + 1])), sc2, ndp);
             float d0, d1;
             unpack2(fmul2(pack2(p0, p1), y2), d0, d1);
-            if (MODE_KV) pk[c * 16 + g * 4 + (t >> 1)] = pack_bf16x2(p0, p1);
-            dk[c * 16 + g * 4 + (t >> 1)] = pack_bf16x2(d0, d1);
+            if (MODE_KV) pk[c * 16 + (j >> 1)] = pack_bf16x2(p0, p1);
+            dk[c * 16 + (j >> 1)] = pack_bf16x2(d0, d1);
           }
+        if (tr) BVC_TR(half, g, 3);
+        if (g > 0) {
+          mbar_wait(pds_free, (uint32_t)(g - 1) & 1u);  // previous dV/dK/dQ MMAs finished reading P / dS
+          tc_fence_after();
         }
-      if (i > 0) {
-        mbar_wait(pds_free, (uint32_t)(i - 1) & 1u);  // previous dV/dK/dQ MMAs finished reading P / dS
-        tc_fence_after();
+        if (tr) BVC_TR(half, g, 4);
+        if (MODE_KV) tmem_st_32x32b_x32(tP + lane_base + half * 32, pk);
+        tmem_st_32x32b_x32(tDS + lane_base + half * 32, dk);
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(pds_full);
+        if (tr) BVC_TR(half, g, 5);
       }
-      if (MODE_KV) tmem_st_32x32b_x32(tP + lane_base + half * 32, pk);
-      tmem_st_32x32b_x32(tDS + lane_base + half * 32, dk);
-      tmem_st_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(pds_full);
-    }
-    // epilogue: the accumulators (rows = owned tile rows, 64 cols); this warp writes 32 of the 64 columns
-    mbar_wait(pds_free, (uint32_t)(n_it - 1) & 1u);
-    tc_fence_after();
-    const int rg = own0 + row;
-    const long long tok = (long long)b * S + rg;
-    auto store32 = [&](uint32_t tacc, int which) {
-      uint32_t ov[32];
-      tmem_ld_32x32b_x32(tacc + lane_base + half * 32, ov);
-      tmem_ld_wait();
-      if (rg < S) {
-        bf16* dst = dqkv + ((tok * 3 + which) * H + h) * 64 + half * 32;
+      // item epilogue: accumulators (rows = owned tile rows, 64 columns) -> bf16 -> the finished item's resident-tile
+      // buffer (no MMA reads it any more) in the 128B-swizzled layout -> ONE TMA store per accumulator, which also
+      // clips the rows past the end of the sequence.  (Direct st.global from the one-row-per-lane TMEM layout touches
+      // 32 cache lines per instruction: trace 2500-3400 clk per item.)  The MMA warp is already issuing the next item's
+      // first S / dP; its first accumulating MMA (which overwrites the accumulators) waits for this warp's next
+      // pds_full arrival, i.e. until after these loads.
+      mbar_wait(pds_free, (uint32_t)(g - 1) & 1u);
+      if (lane == 0 && q4 == 0) BVC_TR(half, g - 1, 6);
+      tc_fence_after();
+      uint8_t* stage = sR + (k & 1) * 2 * kTileBytes;
+      auto stage32 = [&](uint32_t tacc, uint8_t* dst_tile) {
+        uint32_t ov[32];
+        tmem_ld_32x32b_x32(tacc + lane_base + half * 32, ov);
+        tmem_ld_wait();
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
+        for (int gq = 0; gq < 4; ++gq) {
           uint4 o4;
-          o4.x = pack_bf16x2(__uint_as_float(ov[g * 8 + 0]), __uint_as_float(ov[g * 8 + 1]));
-          o4.y = pack_bf16x2(__uint_as_float(ov[g * 8 + 2]), __uint_as_float(ov[g * 8 + 3]));
-          o4.z = pack_bf16x2(__uint_as_float(ov[g * 8 + 4]), __uint_as_float(ov[g * 8 + 5]));
-          o4.w = pack_bf16x2(__uint_as_float(ov[g * 8 + 6]), __uint_as_float(ov[g * 8 + 7]));
-          *reinterpret_cast<uint4*>(dst + g * 8) = o4;
+          o4.x = pack_bf16x2(__uint_as_float(ov[gq * 8 + 0]), __uint_as_float(ov[gq * 8 + 1]));
+          o4.y = pack_bf16x2(__uint_as_float(ov[gq * 8 + 2]), __uint_as_float(ov[gq * 8 + 3]));
+          o4.z = pack_bf16x2(__uint_as_float(ov[gq * 8 + 4]), __uint_as_float(ov[gq * 8 + 5]));
+          o4.w = pack_bf16x2(__uint_as_float(ov[gq * 8 + 6]), __uint_as_float(ov[gq * 8 + 7]));
+          *reinterpret_cast<uint4*>(dst_tile + row * 128 + (((half * 4 + gq) ^ (row & 7)) << 4)) = o4;
         }
+      };
+      stage32(tA0, stage);
+      if (MODE_KV) stage32(tA1, stage + kTileBytes);
+      tc_fence_before();  // the accumulator loads are ordered before this warp's next pds_full arrival
+      fence_async_smem();
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (ct == 0) {
+        if (MODE_KV) {
+          tma_store_4d(&tm_dqkv, stage, 0, 2 * H + h, own0, b);               // dV
+          tma_store_4d(&tm_dqkv, stage + kTileBytes, 0, H + h, own0, b);      // dK
+        } else {
+          tma_store_4d(&tm_dqkv, stage, 0, h, own0, b);                       // dQ
+        }
+        tma_store_commit();
+        tma_store_wait_read0();
+        mbar_arrive(&r_empty[k & 1]);  // the TMA warp may refill this buffer with the resident tiles of item k + 2
       }
-    };
-    if (MODE_KV) {
-      store32(tA0, 2);  // dV
-      store32(tA1, 1);  // dK
-    } else {
-      store32(tA0, 0);  // dQ
+      if (lane == 0 && q4 == 0) BVC_TR(half, g - 1, 7);
+      l_cur = l_nxt;
+      d_cur = d_nxt;
     }
+    if (ct == 0) tma_store_wait0();  // global writes complete before the CTA exits
   }
 
   tc_fence_before();
@@ -741,10 +867,42 @@ extern "C" int bvc_attn_bwd(const void* qkv, const void* out, const void* dout, 
   if (rc) return rc;
   rc = make_head_tmap(&td, dout, H, S, B);
   if (rc) return rc;
-  dim3 grid((S + kTile - 1) / kTile, H, B);
-  attn_bwd_kernel<1><<<grid, kBwdThreads, kBwdSmem, st>>>(tq, td, lse, delta, (bf16*)dqkv, S, H, scale);
+  const long long n_work = (long long)((S + kTile - 1) / kTile) * H * B;
+  BVC_CHECK_ARG(n_work < (1ll << 30));
+  const int grid = (int)(n_work < num_sms() ? n_work : num_sms());  // persistent: one CTA per SM
+  CUtensorMap tdq;
+  rc = make_head_tmap(&tdq, dqkv, 3 * H, S, B);
+  if (rc) return rc;
+  attn_bwd_kernel<1><<<grid, kBwdThreads, kBwdSmem, st>>>(tq, td, tdq, lse, delta, S, H, (int)n_work, scale);
   BVC_CHECK_LAUNCH();
-  attn_bwd_kernel<0><<<grid, kBwdThreads, kBwdSmem, st>>>(tq, td, lse, delta, (bf16*)dqkv, S, H, scale);
+  attn_bwd_kernel<0><<<grid, kBwdThreads, kBwdSmem, st>>>(tq, td, tdq, lse, delta, S, H, (int)n_work, scale);
   BVC_CHECK_LAUNCH();
   return BVC_OK;
 }
+
+#ifdef BVC_TRACE
+// which: 0 = only the Q pass runs afterwards ... the trace buffer holds whatever pass ran last on CTA 0
+extern "C" int bvc_debug_trace_copy(long long* dst_host, int n) {
+  if (n > kTraceRoles * kTraceTiles * kTracePoints) n = kTraceRoles * kTraceTiles * kTracePoints;
+  return (int)cudaMemcpyFromSymbol(dst_host, g_trace, sizeof(long long) * n);
+}
+extern "C" int bvc_debug_attn_bwd_pass(const void* qkv, const void* dout, const float* lse, const float* delta,
+                                       int32_t B, int32_t S, int32_t H, float scale, void* dqkv, int32_t mode_kv,
+                                       void* stream) {
+  cudaFuncSetAttribute(attn_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem);
+  cudaFuncSetAttribute(attn_bwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem);
+  CUtensorMap tq, td, tdq;
+  if (make_head_tmap(&tq, qkv, 3 * H, S, B) || make_head_tmap(&td, dout, H, S, B) ||
+      make_head_tmap(&tdq, dqkv, 3 * H, S, B))
+    return -1;
+  const long long n_work = (long long)((S + kTile - 1) / kTile) * H * B;
+  const int grid = (int)(n_work < num_sms() ? n_work : num_sms());
+  if (mode_kv)
+    attn_bwd_kernel<1><<<grid, kBwdThreads, kBwdSmem, (cudaStream_t)stream>>>(tq, td, tdq, lse, delta, S, H,
+                                                                             (int)n_work, scale);
+  else
+    attn_bwd_kernel<0><<<grid, kBwdThreads, kBwdSmem, (cudaStream_t)stream>>>(tq, td, tdq, lse, delta, S, H,
+                                                                             (int)n_work, scale);
+  return (int)cudaGetLastError();
+}
+#endif

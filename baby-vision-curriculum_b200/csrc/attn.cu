@@ -64,37 +64,6 @@ __device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-// packed fp32x2 arithmetic (sm_100 FFMA2 / FADD2 / FMUL2): halves the issue slots of the softmax-side math, which is
-// what bounds these kernels at head_dim 64 (ncu: issue-active 43 %, tensor pipe 25 %)
-__device__ __forceinline__ uint64_t pack2(float a, float b) {
-  uint64_t r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
-  return r;
-}
-__device__ __forceinline__ void unpack2(uint64_t v, float& a, float& b) {
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
-}
-__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
-  uint64_t d;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-  return d;
-}
-__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
-  uint64_t d;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
-__device__ __forceinline__ uint64_t fmul2(uint64_t a, uint64_t b) {
-  uint64_t d;
-  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
-__device__ __forceinline__ float fmax3(float a, float b, float c) {
-  float d;
-  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
-  return d;
-}
-
 // K-major operand tile [rows][64]: k-step (16 elements) = +32 bytes inside the swizzle atom
 __device__ __forceinline__ uint64_t desc_k(uint32_t base, int kstep) { return umma_smem_desc(base + kstep * 32, 1024, 16); }
 // MN-major operand tile [k rows][64 mn]: k-step (16 rows) = +2048 bytes; lbo = distance between 64-wide mn blocks
@@ -404,7 +373,8 @@ __global__ void __launch_bounds__(256) attn_delta_kernel(const bf16* __restrict_
   }
 }
 
-// warpgroup 0: warp 0 TMA, warp 1 MMA, warps 2-3 idle; warpgroups 1-2 (warps 4-11): compute.  Launched at the 168
+// warpgroup 0: warp 0 TMA loads, warp 1 MMA issue, warp 2 statistics (MODE_KV), warp 3 TMA stores; warpgroups 1-2
+// (warps 4-11): compute.  Launched at the 168
 // registers/thread that 384 threads allow, then warpgroup 0 shrinks to 88 and the compute warpgroups grow to 208
 // (setmaxnreg): the compute threads hold a 64-wide slice of S and dP plus their packed P / dS outputs in registers.
 constexpr int kBwdThreads = 384;
@@ -426,7 +396,7 @@ constexpr int kBwdRegsCtl = 88, kBwdRegsCompute = 208;
 // products with 1.0 are exact, accumulation is fp32).  The three [128][16] operands live in k-steps 0 / 1 / 2 of one
 // 128B-swizzled [128][64] tile; the compute warps rewrite the two statistic columns once per streamed tile.
 constexpr int kBwdStages = 4;
-constexpr int kBwdSmem = kTileBytes * (4 + 2 * kBwdStages + 1) + 256;
+constexpr int kBwdSmem = kTileBytes * (4 + 2 * kBwdStages + 2) + 256;
 
 template <int MODE_KV>
 __global__ void __launch_bounds__(kBwdThreads, 1)
@@ -437,8 +407,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
   uint8_t* sR = smem;                                      // [2 buffers][R0 | R1]; MODE_KV: K_j, V_j | MODE_Q: Q_i, dO_i
   uint8_t* sX = smem + 4 * kTileBytes;                     // [stages] MODE_KV: Q_i  | MODE_Q: K_j
   uint8_t* sY = smem + (4 + kBwdStages) * kTileBytes;      // [stages] MODE_KV: dO_i | MODE_Q: V_j
-  uint8_t* sAug = smem + (4 + 2 * kBwdStages) * kTileBytes;  // MODE_KV: ones | -lse/scale | -delta (k-steps 0, 1, 2)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (5 + 2 * kBwdStages) * kTileBytes);
+  uint8_t* sAug = smem + (4 + 2 * kBwdStages) * kTileBytes;  // MODE_KV: [2] x (ones | -lse/scale | -delta in k-steps 0, 1, 2)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (6 + 2 * kBwdStages) * kTileBytes);
   uint64_t* r_full = bars + 0;                   // [2]
   uint64_t* r_empty = bars + 2;                  // [2]
   uint64_t* st_full = bars + 4;                  // [stages]
@@ -447,7 +417,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
   uint64_t* sdp_free = sdp_full + 1;
   uint64_t* pds_full = sdp_full + 2;
   uint64_t* pds_free = sdp_full + 3;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sdp_full + 4);
+  uint64_t* aug_full = sdp_full + 4;             // [2]  statistics warp -> MMA warp
+  uint64_t* aug_empty = sdp_full + 6;            // [2]
+  uint64_t* epi_full = sdp_full + 8;             // compute warps -> store warp: an item's accumulators are staged
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sdp_full + 9);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_it = (S + kTile - 1) / kTile;  // tiles per sequence = owned tiles per (clip, head) = streamed tiles per item
@@ -475,6 +448,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
     mbar_init(sdp_free, 8);
     mbar_init(pds_full, 8);
     mbar_init(pds_free, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&aug_full[i], 1);
+      mbar_init(&aug_empty[i], 1);
+    }
+    mbar_init(epi_full, 8);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -528,8 +506,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
       auto valid16 = [&](int i) { return min(kTile, (S - i * kTile + 15) & ~15); };
       // k = 0 descriptors; a K = 16 step moves the start address by 32 B (K-major, +2 in the descriptor's 16-byte
       // units) or by 16 rows = 2048 B (MN-major, +128)
-      const uint64_t dAug = desc_k(smem_u32(sAug), 0);
-      auto issue_s_dp = [&](int k, int i, int st) {
+      auto issue_s_dp = [&](int k, int i, int st, int gg) {
+        const uint64_t dAug = desc_k(smem_u32(sAug + (gg & 1) * kTileBytes), 0);
         const uint32_t idesc_s = umma_idesc_bf16(valid16(i), 0, 0, 128);
         const uint32_t aR = smem_u32(sR + (k & 1) * 2 * kTileBytes);
         const uint64_t dR0 = desc_k(aR, 0), dR1 = desc_k(aR + kTileBytes, 0);
@@ -540,16 +518,18 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
         if (MODE_KV) umma_bf16_ss(tS, dAug, dAug + 2, idesc_s, 1);       // S^T - lse_q / scale
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) umma_bf16_ss(tDP, dR1 + 2 * kk, dY + 2 * kk, idesc_s, kk > 0);
-        if (MODE_KV) umma_bf16_ss(tDP, dAug, dAug + 4, idesc_s, 1);      // dP^T - delta_q
+        if (MODE_KV) {
+          umma_bf16_ss(tDP, dAug, dAug + 4, idesc_s, 1);                 // dP^T - delta_q
+          umma_commit(&aug_empty[gg & 1]);
+        }
       };
-      // the compute warps have written the augmentation tile (ones + tile 0's statistics)
-      if (MODE_KV) asm volatile("bar.sync 2, 288;" ::: "memory");
       if (n_glob > 0) {
         mbar_wait(&r_full[0], 0);
         mbar_wait(&st_full[0], 0);
+        if (MODE_KV) mbar_wait(&aug_full[0], 0);
         tc_fence_after();
         if (elect_one()) {
-          issue_s_dp(0, 0, 0);
+          issue_s_dp(0, 0, 0, 0);
           umma_commit(sdp_full);
         }
         __syncwarp();
@@ -566,12 +546,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
           const int st1 = (g + 1) % kBwdStages;
           if (i1 == 0) mbar_wait(&r_full[k1 & 1], (uint32_t)(k1 >> 1) & 1u);
           mbar_wait(&st_full[st1], (uint32_t)((g + 1) / kBwdStages) & 1u);
+          if (MODE_KV) mbar_wait(&aug_full[(g + 1) & 1], (uint32_t)((g + 1) >> 1) & 1u);
           if (lane == 0) BVC_TR(2, g, 1);
           mbar_wait(sdp_free, (uint32_t)g & 1u);
           if (lane == 0) BVC_TR(2, g, 2);
           tc_fence_after();
           if (elect_one()) {
-            issue_s_dp(k1, i1, st1);
+            issue_s_dp(k1, i1, st1, g + 1);
             umma_commit(sdp_full);
           }
           __syncwarp();
@@ -618,6 +599,81 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
         k = k1;
         i = i1;
       }
+    } else if (warp == 2) {
+      // statistics warp (MODE_KV): per streamed tile, the three-way bf16 split of -lse/scale and -delta of its 128
+      // queries into k-steps 1 / 2 (16-byte chunks 2 / 4 of the 128B-swizzled rows) of the augmentation tile g & 1;
+      // k-step 0 holds the constant ones.  Lane l owns queries 4l .. 4l+3.
+      if (MODE_KV) {
+        const uint4 ones = make_uint4(pack_bf16x2(1.f, 1.f), pack_bf16x2(1.f, 0.f), 0u, 0u);
+        const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+        for (int r = lane; r < 2 * kTile; r += 32) {  // both tiles are contiguous: 256 rows of 128 bytes
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+            if (c != 2 && c != 4) *reinterpret_cast<uint4*>(sAug + r * 128 + ((c ^ (r & 7)) << 4)) = c == 0 ? ones : zero;
+        }
+        float cur[8], nxt[8];
+        auto load8 = [&](int kk, int ii, float (&v)[8]) {
+          const float* lb = lse + (long long)item_bh(kk) * S;
+          const float* db = delta + (long long)item_bh(kk) * S;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int qg = min(ii * kTile + lane * 4 + j, S - 1);
+            v[j] = __ldg(lb + qg);
+            v[4 + j] = __ldg(db + qg);
+          }
+        };
+        int k = 0, i = 0;
+        if (n_glob > 0) load8(0, 0, cur);
+        for (int g = 0; g < n_glob; ++g) {
+          int k1 = k, i1 = i + 1;
+          if (i1 == n_it) {
+            i1 = 0;
+            ++k1;
+          }
+          if (g + 1 < n_glob) load8(k1, i1, nxt);  // in flight while this tile is written
+          mbar_wait(&aug_empty[g & 1], ((uint32_t)(g >> 1) & 1u) ^ 1u);
+          uint8_t* tile = sAug + (g & 1) * kTileBytes;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int r = lane * 4 + (j & 3);
+            const float v = j < 4 ? -cur[j] / scale : -cur[j];
+            const float hi = __bfloat162float(__float2bfloat16_rn(v));
+            const float r1 = v - hi;
+            const float mid = __bfloat162float(__float2bfloat16_rn(r1));
+            const float lo = r1 - mid;
+            *reinterpret_cast<uint4*>(tile + r * 128 + (((j < 4 ? 2 : 4) ^ (r & 7)) << 4)) =
+                make_uint4(pack_bf16x2(hi, mid), pack_bf16x2(lo, 0.f), 0u, 0u);
+          }
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&aug_full[g & 1]);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) cur[j] = nxt[j];
+          k = k1;
+          i = i1;
+        }
+      }
+    } else {
+      // store warp: one TMA store per staged accumulator (it also clips the rows past the end of the sequence), then
+      // the resident-tile buffer that served as staging goes back to the TMA warp
+      for (int k = 0; k < n_my; ++k) {
+        const int own0 = item_tile(k) * kTile, bh = item_bh(k), h = bh % H, b = bh / H;
+        uint8_t* stage = sR + (k & 1) * 2 * kTileBytes;
+        mbar_wait(epi_full, (uint32_t)k & 1u);
+        if (lane == 0) {
+          if (MODE_KV) {
+            tma_store_4d(&tm_dqkv, stage, 0, 2 * H + h, own0, b);               // dV
+            tma_store_4d(&tm_dqkv, stage + kTileBytes, 0, H + h, own0, b);      // dK
+          } else {
+            tma_store_4d(&tm_dqkv, stage, 0, h, own0, b);                       // dQ
+          }
+          tma_store_commit();
+          tma_store_wait_read0();
+          mbar_arrive(&r_empty[k & 1]);  // the TMA warp may refill this buffer with the resident tiles of item k + 2
+        }
+        __syncwarp();
+      }
+      if (lane == 0) tma_store_wait0();  // global writes complete before the CTA exits
     }
   } else {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kBwdRegsCompute));
@@ -635,23 +691,6 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
     const uint32_t lane_base = (uint32_t)(q4 * 32) << 16;
     const float c_log2 = scale * kLog2e;
     const uint64_t cl2 = pack2(c_log2, c_log2), sc2 = pack2(scale, scale);
-    // MODE_KV: compute thread ct owns statistic (ct < 128 ? lse : delta) of query ct % 128 of every streamed tile and
-    // writes its three-way bf16 split into row ct % 128 of the augmentation tile (k-step 1 resp. 2 = 16-byte chunk
-    // 2 resp. 4 of the 128B-swizzled row; the second chunk of each k-step stays zero)
-    const int arow = ct & 127;
-    uint8_t* aug_dst = sAug + arow * 128 + ((((ct < 128) ? 2 : 4) ^ (arow & 7)) << 4);
-    auto load_stat = [&](int kk, int ii) {
-      const int qg = min(ii * kTile + arow, S - 1);
-      return __ldg((ct < 128 ? lse : delta) + (long long)item_bh(kk) * S + qg);
-    };
-    auto put_aug = [&](float v) {
-      v = ct < 128 ? -v / scale : -v;
-      const float hi = __bfloat162float(__float2bfloat16_rn(v));
-      const float r1 = v - hi;
-      const float mid = __bfloat162float(__float2bfloat16_rn(r1));
-      const float lo = r1 - mid;
-      *reinterpret_cast<uint4*>(aug_dst) = make_uint4(pack_bf16x2(hi, mid), pack_bf16x2(lo, 0.f), 0u, 0u);
-    };
     // MODE_Q: this thread's row statistics of item kk
     auto load_row = [&](int kk, float& l, float& d) {
       const int qc = min(item_tile(kk) * kTile + row, S - 1);
@@ -659,32 +698,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
       l = __ldg(lse + o);
       d = __ldg(delta + o);
     };
-    float st_next = 0.f, l_cur = 0.f, d_cur = 0.f;
-    int sk = 0, si = 0;  // (item, tile) whose statistic st_next holds: always the tile after the one being computed
-    auto stat_advance = [&]() {
-      if (++si == n_it) {
-        si = 0;
-        ++sk;
-      }
-    };
-    if (MODE_KV) {
-      if (ct < 128) {  // constant part of the augmentation tile: ones in k-step 0, zeros in every other static chunk
-        const uint4 ones = make_uint4(pack_bf16x2(1.f, 1.f), pack_bf16x2(1.f, 0.f), 0u, 0u);
-        const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
-#pragma unroll
-        for (int c = 0; c < 8; ++c)
-          if (c != 2 && c != 4) *reinterpret_cast<uint4*>(sAug + arow * 128 + ((c ^ (arow & 7)) << 4)) = c == 0 ? ones : zero;
-      }
-      if (n_glob > 0) {
-        put_aug(load_stat(0, 0));
-        stat_advance();
-        if (n_glob > 1) st_next = load_stat(sk, si);
-      }
-      fence_async_smem();
-      asm volatile("bar.sync 2, 288;" ::: "memory");  // with the MMA warp, once
-    } else if (n_glob > 0) {
-      load_row(0, l_cur, d_cur);
-    }
+    float l_cur = 0.f, d_cur = 0.f;
+    if (!MODE_KV && n_glob > 0) load_row(0, l_cur, d_cur);
     int g = 0;
     for (int k = 0; k < n_my; ++k) {
       const int own0 = item_tile(k) * kTile, bh = item_bh(k), h = bh % H, b = bh / H;
@@ -702,14 +717,6 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
         mbar_wait(sdp_full, (uint32_t)g & 1u);
         if (tr) BVC_TR(half, g, 1);
         tc_fence_after();
-        if (MODE_KV && g + 1 < n_glob) {
-          // tile g's score MMAs are done reading the statistic columns: write tile g+1's (read by the S / dP MMAs
-          // that the MMA warp issues once this warp has arrived on sdp_free below)
-          put_aug(st_next);
-          fence_async_smem();
-          stat_advance();
-          if (g + 2 < n_glob) st_next = load_stat(sk, si);  // in flight during this tile's math
-        }
         uint32_t sv[2][32], dv[2][32];
 #pragma unroll
         for (int c = 0; c < 2; ++c) tmem_ld_32x32b_x32(tS + lane_base + half * 64 + c * 32, sv[c]);
@@ -787,23 +794,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
       if (MODE_KV) stage32(tA1, stage + kTileBytes);
       tc_fence_before();  // the accumulator loads are ordered before this warp's next pds_full arrival
       fence_async_smem();
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      if (ct == 0) {
-        if (MODE_KV) {
-          tma_store_4d(&tm_dqkv, stage, 0, 2 * H + h, own0, b);               // dV
-          tma_store_4d(&tm_dqkv, stage + kTileBytes, 0, H + h, own0, b);      // dK
-        } else {
-          tma_store_4d(&tm_dqkv, stage, 0, h, own0, b);                       // dQ
-        }
-        tma_store_commit();
-        tma_store_wait_read0();
-        mbar_arrive(&r_empty[k & 1]);  // the TMA warp may refill this buffer with the resident tiles of item k + 2
-      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(epi_full);  // the store warp takes it from here
       if (lane == 0 && q4 == 0) BVC_TR(half, g - 1, 7);
       l_cur = l_nxt;
       d_cur = d_nxt;
     }
-    if (ct == 0) tma_store_wait0();  // global writes complete before the CTA exits
   }
 
   tc_fence_before();

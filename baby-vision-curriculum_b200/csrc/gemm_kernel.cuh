@@ -79,6 +79,49 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
   return fmaf(x, pdf, cdf);
 }
 
+// ---- two elements at a time on the packed fp32x2 pipe (interior-tile fast path of the epilogue) ----
+// Phi(-|x|) for a pair: the same degree-7 fit as phi_neg_abs, 7 FFMA2 + 2 MUFU.EX2
+__device__ __forceinline__ uint64_t phi_neg_abs2(uint64_t a2) {
+  uint64_t q = pack2(-1.8348840982e-06f, -1.8348840982e-06f);
+  q = ffma2(q, a2, pack2(6.1599723096e-05f, 6.1599723096e-05f));
+  q = ffma2(q, a2, pack2(-9.3053573547e-04f, -9.3053573547e-04f));
+  q = ffma2(q, a2, pack2(8.5079311974e-03f, 8.5079311974e-03f));
+  q = ffma2(q, a2, pack2(-5.3960143443e-02f, -5.3960143443e-02f));
+  q = ffma2(q, a2, pack2(-4.5846433058e-01f, -4.5846433058e-01f));
+  q = ffma2(q, a2, pack2(-1.1512510639e+00f, -1.1512510639e+00f));
+  q = ffma2(q, a2, pack2(-9.9999529365e-01f, -9.9999529365e-01f));
+  float q0, q1;
+  unpack2(q, q0, q1);
+  return pack2(exp2f(q0), exp2f(q1));
+}
+__device__ __forceinline__ uint64_t abs2(uint64_t x2) { return x2 & 0x7fffffff7fffffffull; }
+// gelu(x) = x Phi(x) = 0.5 x + |x| (0.5 - Phi(-|x|))   (no compare / select)
+__device__ __forceinline__ uint64_t gelu_erf2(uint64_t x2) {
+  const uint64_t a2 = abs2(x2);
+  const uint64_t half2 = pack2(0.5f, 0.5f);
+  const uint64_t t2 = ffma2(phi_neg_abs2(a2), pack2(-1.f, -1.f), half2);  // 0.5 - w
+  return ffma2(x2, half2, fmul2(a2, t2));
+}
+// gelu'(x) = Phi(x) + x phi(x),  Phi(x) = 0.5 + copysign(0.5 - Phi(-|x|), x)
+__device__ __forceinline__ uint64_t gelu_erf_grad2(uint64_t x2) {
+  const uint64_t a2 = abs2(x2);
+  const uint64_t half2 = pack2(0.5f, 0.5f);
+  const uint64_t t2 = ffma2(phi_neg_abs2(a2), pack2(-1.f, -1.f), half2);  // 0.5 - w  (>= 0)
+  const uint64_t cdf2 = fadd2(half2, t2 | (x2 & 0x8000000080000000ull));
+  float e0, e1;
+  unpack2(fmul2(fmul2(x2, x2), pack2(-0.72134752044448170f, -0.72134752044448170f)), e0, e1);
+  const uint64_t pdf2 = fmul2(pack2(exp2f(e0), exp2f(e1)), pack2(0.3989422804014327f, 0.3989422804014327f));
+  return ffma2(x2, pdf2, cdf2);
+}
+__device__ __forceinline__ uint64_t bf16x2_to_f32x2(uint32_t h) {
+  return pack2(__uint_as_float(h << 16), __uint_as_float(h & 0xffff0000u));
+}
+__device__ __forceinline__ uint32_t f32x2_to_bf16x2(uint64_t v) {
+  float a, b;
+  unpack2(v, a, b);
+  return pack_bf16x2(a, b);
+}
+
 template <int BN, int A_MN, int B_MN, int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
@@ -220,6 +263,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     const int rsub = lane >> 3;      // phase 2: row within each group of 4 rows
     const float alpha = p.alpha * (p.alpha_dev ? __ldg(p.alpha_dev) : 1.0f);
     constexpr bool G = EPI == EPI_GENERIC;
+    constexpr bool kFast = EPI == EPI_PLAIN || EPI == EPI_GELU || EPI == EPI_DGELU || EPI == EPI_RES;
+    const bool has_alpha = alpha != 1.0f;
     const bool kSplit = G ? p.k_splits > 1 : EPI == EPI_SPLITK;
     const bool kGelu = G ? p.act == 1 : EPI == EPI_GELU;
     const bool kDgelu = G ? p.act == 2 : EPI == EPI_DGELU;
@@ -238,6 +283,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const int rbase = m0 + q * 32;
+      const bool interior = m0 + BM <= p.M && n0 + BN <= p.N;  // warp-uniform
       float lsum = 0.f;
 #pragma unroll 1
       for (int cc = 0; cc < kColsPerWarp; cc += 32) {
@@ -256,6 +302,88 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
               make_uint4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
         __syncwarp();
         const int col = n0 + c_tile + c4 * 4;
+        if (kFast && interior) {
+          // ---------------------------------------------------------------- interior tile, non-generic variant:
+          // no row / column guards, no segment remap, pointers advance by a constant stride, math on fp32x2 pairs.
+          // (The guarded path below costs ~30 instructions per output element on the GELU variant -- ncu: FFMA 8,
+          // IMAD/IADD3/ISETP/BRA 9 -- which made the K = 384 decoder GEMMs epilogue-bound.)
+          const long long r0 = rbase + rsub;
+          uint64_t b01 = 0, b23 = 0;
+          if (p.bias) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+            b01 = pack2(b4.x, b4.y);
+            b23 = pack2(b4.z, b4.w);
+          }
+          const uint64_t al2 = pack2(alpha, alpha);
+          float4 pre_f[8];
+          uint2 pre_h[8];
+          if (EPI == EPI_RES) {
+            const float* fb = p.res + r0 * p.ldr + col;
+#pragma unroll
+            for (int it = 0; it < 8; ++it)
+              asm volatile("ld.volatile.global.v4.f32 {%0, %1, %2, %3}, [%4];"
+                           : "=f"(pre_f[it].x), "=f"(pre_f[it].y), "=f"(pre_f[it].z), "=f"(pre_f[it].w)
+                           : "l"(fb + (long long)it * 4 * p.ldr)
+                           : "memory");
+            asm volatile("" ::"f"(pre_f[0].x), "f"(pre_f[1].x), "f"(pre_f[2].x), "f"(pre_f[3].x), "f"(pre_f[4].x),
+                         "f"(pre_f[5].x), "f"(pre_f[6].x), "f"(pre_f[7].x));
+          }
+          if (EPI == EPI_DGELU) {
+            const bf16* hb = p.aux_in + r0 * p.ld_aux + col;
+#pragma unroll
+            for (int it = 0; it < 8; ++it)
+              asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];"
+                           : "=r"(pre_h[it].x), "=r"(pre_h[it].y)
+                           : "l"(hb + (long long)it * 4 * p.ld_aux)
+                           : "memory");
+            asm volatile("" ::"r"(pre_h[0].x), "r"(pre_h[1].x), "r"(pre_h[2].x), "r"(pre_h[3].x), "r"(pre_h[4].x),
+                         "r"(pre_h[5].x), "r"(pre_h[6].x), "r"(pre_h[7].x));
+          }
+          // the dispatcher (gemm.cu) guarantees: EPI_RES writes fp32 only, the other fast variants bf16 only
+          bf16* ob = EPI != EPI_RES ? p.out_bf16 + r0 * p.ldo + col : nullptr;
+          float* of = EPI == EPI_RES ? p.out_f32 + r0 * p.ldo + col : nullptr;
+          bf16* oa = (EPI == EPI_GELU && p.aux_out) ? p.aux_out + r0 * p.ld_aux + col : nullptr;
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int rl = it * 4 + rsub;
+            const float4 t = *reinterpret_cast<const float4*>(stg + rl * 128 + ((c4 ^ (rl & 7)) << 4));
+            uint64_t v01 = pack2(t.x, t.y), v23 = pack2(t.z, t.w);
+            if (has_alpha) {
+              v01 = fmul2(v01, al2);
+              v23 = fmul2(v23, al2);
+            }
+            v01 = fadd2(v01, b01);
+            v23 = fadd2(v23, b23);
+            if (EPI == EPI_GELU) {
+              uint2 pk;
+              pk.x = f32x2_to_bf16x2(v01);
+              pk.y = f32x2_to_bf16x2(v23);
+              if (oa) *reinterpret_cast<uint2*>(oa + (long long)it * 4 * p.ld_aux) = pk;
+              v01 = gelu_erf2(bf16x2_to_f32x2(pk.x));
+              v23 = gelu_erf2(bf16x2_to_f32x2(pk.y));
+            } else if (EPI == EPI_DGELU) {
+              v01 = fmul2(v01, gelu_erf_grad2(bf16x2_to_f32x2(pre_h[it].x)));
+              v23 = fmul2(v23, gelu_erf_grad2(bf16x2_to_f32x2(pre_h[it].y)));
+            } else if (EPI == EPI_RES) {
+              v01 = fadd2(v01, pack2(pre_f[it].x, pre_f[it].y));
+              v23 = fadd2(v23, pack2(pre_f[it].z, pre_f[it].w));
+            }
+            if (EPI == EPI_RES) {
+              float x0, x1, x2, x3;
+              unpack2(v01, x0, x1);
+              unpack2(v23, x2, x3);
+              *reinterpret_cast<float4*>(of + (long long)it * 4 * p.ldo) = make_float4(x0, x1, x2, x3);
+            }
+            if (EPI != EPI_RES) {
+              uint2 pk;
+              pk.x = f32x2_to_bf16x2(v01);
+              pk.y = f32x2_to_bf16x2(v23);
+              *reinterpret_cast<uint2*>(ob + (long long)it * 4 * p.ldo) = pk;
+            }
+          }
+          __syncwarp();
+          continue;
+        }
         if (col < p.N) {
           float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
           if (p.bias) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));

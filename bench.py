@@ -12,7 +12,8 @@ value : whole-job clips/s with the clips and masks already resident in HBM (a 61
         > the 126 MB L2, re-read from HBM every step).
 e2e   : the same loop through the public API from HOST buffers: every step copies its fp32 clip batch and bool mask
         from pinned host memory (prefetched one step ahead on a copy stream) and reads the loss back to the host.
-roofline     : per-kernel CUDA-event timing of every libbvc.so launch inside the timed steps (bvc_b200._lib profiler).
+roofline     : per-kernel CUDA-event timing of every libbvc.so launch (bvc_b200._lib profiler) in a second timed pass of
+               the same K steps, so the event records do not slow the pass that produces `value`.
 cpu_baseline : the reference's own CPU path (HF transformers VideoMAEForPreTraining, fp32) on this box's host cores,
                bounded sample.   --impl reference prints that as its own line.
 """
@@ -229,8 +230,6 @@ def run_ours(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    records = []
-    L.set_profiler(records)
     n0 = L.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -239,11 +238,24 @@ def run_ours(args):
         loss = train_step(dev_clips[i % n_pool], dev_masks[i % 8])
     e1.record()
     barrier()
-    L.set_profiler(None)
     launches = L.launch_count() - n0
-    clocks = sampler.stop() if rank == 0 else None
     ms = e0.elapsed_time(e1)
     last_loss = float(loss.detach())
+    # ------------------------------------------------------------------ the same K steps again, every libbvc.so launch
+    # bracketed by CUDA events on its stream (per-kernel durations for the roofline).  Kept out of the pass that
+    # produces `value`: ~750 event records per step cost ~4 % of the step (reported as ms_per_step_profiled).
+    records = []
+    L.set_profiler(records)
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    p0.record()
+    for i in range(args.steps):
+        train_step(dev_clips[i % n_pool], dev_masks[i % 8])
+    p1.record()
+    barrier()
+    L.set_profiler(None)
+    ms_prof = p0.elapsed_time(p1)
+    clocks = sampler.stop() if rank == 0 else None
 
     # ------------------------------------------------------------------ host-buffer loop (e2e)
     copy_stream = torch.cuda.Stream(device=dev)
@@ -317,7 +329,9 @@ def run_ours(args):
         roof = {"bound": top["bound"], "achieved": top["achieved"], "peak": top["peak"], "unit": top["unit"],
                 "frac": top["frac"], "traffic": None, "kernel": top["kernel"],
                 "peak_source": f"MEASURED_PEAKS.json ({peaks['src']}; sustained bf16 figure: kernel timed inside a long step)",
-                "share_of_step": top["ms_per_step"] / (ms / args.steps)}
+                "share_of_step": top["ms_per_step"] / (ms_prof / args.steps),
+                "measured_in": "second timed pass of the same K steps with a CUDA event pair around every libbvc.so "
+                               "launch (ms_per_step_profiled); `value` comes from the first pass, without them"}
         step_flops = flops_per_clip(c) * B
         cpu = cpu_reference(args.config, args.cpu_batch, args.cpu_steps, 1) if not args.no_cpu else None
         clips = B * world
@@ -331,6 +345,7 @@ def run_ours(args):
                                    f"tube mask 0.9, batch {B}/GPU",
                        "global_batch": clips, "parallelism": f"dp{world}" + (f" ({args.ddp} DDP)" if world > 1 else ""), "l2": "inputs larger than L2 "
                        "(616 MB clip batch per step, alternating between two resident batches)"},
+            "ms_per_step_profiled": ms_prof / args.steps,
             "model_tflops_per_gpu": step_flops / (ms / args.steps) / 1e9,
             "model_tc_frac": step_flops / (ms / args.steps) / 1e9 / peaks["tc"],
             "e2e": {"value": clips * args.steps / (ms_e2e / 1e3), "unit": "clips/s",

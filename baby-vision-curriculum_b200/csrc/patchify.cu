@@ -2,7 +2,7 @@
 //
 //   bvc_mask_count / bvc_mask_to_index : one warp per clip, ballot + popc prefix; bit-exact replacement of the
 //       boolean-index ops (HF:121-122, 587-588, 669-670).
-//   bvc_patchify_target : one CTA per (clip, temporal slot, row of patches).  A single 5-D TMA box
+//   bvc_patchify_target : persistent CTAs over (clip, temporal slot, row of patches, column split).  A 5-D TMA box
 //       (W x 16 rows x 3 channels x ts frames) stages the row in shared memory; each warp then owns whole
 //       tubelets: visible ones are emitted as bf16 GEMM rows in Conv3d K-order (c,t,ph,pw), masked ones get their
 //       per-channel mean / unbiased variance over the ts*256 pixels (two-pass, from registers) and are emitted as
@@ -59,102 +59,134 @@ __global__ void mask_to_index_kernel(const uint8_t* __restrict__ mask, int B, in
 __device__ __constant__ float kInStd[3] = {0.229f, 0.224f, 0.225f};
 __device__ __constant__ float kInMean[3] = {0.485f, 0.456f, 0.406f};
 
-// smem layout of the staged box: [t][c][ph][w] fp32, w = 0..W-1
+// Persistent, TMA-staged: one CTA per SM walks work items (clip, temporal slot, row of patches, column split).  Warp 0
+// streams 5-D TMA boxes  [TS frames][3 channels][16 rows][BW pixels] fp32  through a ring of shared-memory stages
+// (mbarrier full / empty), so ~130 KB of loads are in flight per SM at all times; 7 consumer warps take whole tubelets
+// out of a landed box.  A lane holds 4 consecutive pixels of one image row for every (frame, channel) plane -- which
+// is exactly 3 consecutive float4 of the (t, ph, pw, c)-ordered target row per (frame, row) -- so the normalised target
+// is written straight from registers (no shared-memory re-read, no index arithmetic), and the visible tubelets as
+// bf16 rows in Conv3d K-order.  The first version (one CTA per box, load -> compute -> store in sequence, targets
+// re-read element-wise from shared memory) reached 3.5 TB/s; HBM: 18.78 MB per clip.
+constexpr int kPatchConsumers = 7;
+constexpr int kPatchThreads = 32 * (1 + kPatchConsumers);
+
 template <int TS>
-__global__ void __launch_bounds__(256) patchify_target_kernel(const __grid_constant__ CUtensorMap tmap,
-                                                              const int* __restrict__ slot, int Tg, int Hg, int Wg,
-                                                              int W, int nv, int N, bf16* __restrict__ patches_vis,
-                                                              float* __restrict__ target, int norm_pix) {
+__global__ void __launch_bounds__(kPatchThreads, 1) patchify_target_kernel(const __grid_constant__ CUtensorMap tmap,
+                                                                           const int* __restrict__ slot, int Tg, int Hg,
+                                                                           int Wg, int split, int n_items, int n_stages,
+                                                                           int nv, int N, bf16* __restrict__ patches_vis,
+                                                                           float* __restrict__ target, int norm_pix) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
-  float* tile = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
-  __shared__ uint64_t bar;
-  const int hg = blockIdx.x % Hg;
-  const int tg = (blockIdx.x / Hg) % Tg;
-  const int b = blockIdx.x / (Hg * Tg);
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  const int TB = Wg / split;   // tubelets per box
+  const int BW = TB * 16;      // pixels per box row
+  const int box_bytes = TS * 3 * 16 * BW * 4;
+  uint64_t* full = reinterpret_cast<uint64_t*>(base + (size_t)n_stages * box_bytes);
+  uint64_t* empty = full + n_stages;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    mbar_init(&bar, 1);
+    tma_prefetch_desc(&tmap);
+    for (int i = 0; i < n_stages; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], kPatchConsumers);
+    }
     fence_mbar_init();
-    mbar_expect_tx(&bar, (uint32_t)(TS * 3 * 16 * W * 4));
-    tma_load_5d(tile, &tmap, &bar, 0, hg * 16, 0, tg * TS, b);
   }
   __syncthreads();
-  mbar_wait(&bar, 0);
 
   constexpr int K = 3 * TS * 256;
   constexpr int NI = TS * 6;  // 8-row groups per tubelet: TS*3 planes x 2
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int nm = N - nv;
-  const int sub_row = lane >> 2, chunk = lane & 3;
-  for (int wg = warp; wg < Wg; wg += nwarps) {
-    const int n = (tg * Hg + hg) * Wg + wg;
-    const int s = __ldg(slot + (long long)b * N + n);
-    if (s < 0 || s >= N) continue;  // malformed mask row: flagged by bvc_mask_to_index, nothing is written
-    float4 v[NI];
-#pragma unroll
-    for (int i = 0; i < NI; ++i) {
-      const int row = i * 8 + sub_row;  // = (t*3 + c)*16 + ph
-      v[i] = *reinterpret_cast<const float4*>(tile + (long long)row * W + wg * 16 + chunk * 4);
+  if (warp == 0) {
+    if (lane == 0) {
+      int it = 0;
+      for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
+        const int sp = w % split, hg = (w / split) % Hg, tg = (w / (split * Hg)) % Tg, b = w / (split * Hg * Tg);
+        const int st = it % n_stages;
+        mbar_wait(&empty[st], ((uint32_t)(it / n_stages) & 1u) ^ 1u);
+        mbar_expect_tx(&full[st], (uint32_t)box_bytes);
+        tma_load_5d(base + (size_t)st * box_bytes, &tmap, &full[st], sp * BW, hg * 16, 0, tg * TS, b);
+      }
     }
-    if (s < nv) {
-      // visible: bf16 row in Conv3d K-order k = ((c*TS + t)*16 + ph)*16 + pw
-      bf16* dst = patches_vis + ((long long)b * nv + s) * K;
+  } else {
+    const int cw = warp - 1;
+    const int sub_row = lane >> 2, chunk = lane & 3;
+    int it = 0;
+    for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
+      const int sp = w % split, hg = (w / split) % Hg, tg = (w / (split * Hg)) % Tg, b = w / (split * Hg * Tg);
+      const int st = it % n_stages;
+      const float* tile = reinterpret_cast<const float*>(base + (size_t)st * box_bytes);
+      mbar_wait(&full[st], (uint32_t)(it / n_stages) & 1u);
+      for (int wl = cw; wl < TB; wl += kPatchConsumers) {
+        const int n = (tg * Hg + hg) * Wg + sp * TB + wl;
+        const int s = __ldg(slot + (long long)b * N + n);
+        if (s < 0 || s >= N) continue;  // malformed mask row: flagged by bvc_mask_to_index, nothing is written
+        float4 v[NI];
 #pragma unroll
-      for (int i = 0; i < NI; ++i) {
-        const int plane = i >> 1;  // t*3 + c
-        const int t = plane / 3, c = plane % 3;
-        const int ph = (i & 1) * 8 + sub_row;
-        uint2 pk;
-        pk.x = pack_bf16x2(v[i].x, v[i].y);
-        pk.y = pack_bf16x2(v[i].z, v[i].w);
-        *reinterpret_cast<uint2*>(dst + ((c * TS + t) * 16 + ph) * 16 + chunk * 4) = pk;
-      }
-    } else {
-      // masked: per-channel statistics over TS*256 pixels, two-pass from registers
-      float mean[3], inv[3];
+        for (int i = 0; i < NI; ++i) {
+          const int row = i * 8 + sub_row;  // = (t*3 + c)*16 + ph
+          v[i] = *reinterpret_cast<const float4*>(tile + (long long)row * BW + wl * 16 + chunk * 4);
+        }
+        if (s < nv) {
+          // visible: bf16 row in Conv3d K-order k = ((c*TS + t)*16 + ph)*16 + pw
+          bf16* dst = patches_vis + ((long long)b * nv + s) * K;
 #pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        float sum = 0.f;
-#pragma unroll
-        for (int i = 0; i < NI; ++i)
-          if ((i >> 1) % 3 == c) sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
-        const float mu = warp_sum(sum) * (1.0f / (TS * 256));
-        float ss = 0.f;
-#pragma unroll
-        for (int i = 0; i < NI; ++i)
-          if ((i >> 1) % 3 == c) {
-            const float a = v[i].x - mu, bb = v[i].y - mu, cc = v[i].z - mu, dd = v[i].w - mu;
-            ss += (a * a + bb * bb) + (cc * cc + dd * dd);
+          for (int i = 0; i < NI; ++i) {
+            const int plane = i >> 1;  // t*3 + c
+            const int t = plane / 3, c = plane % 3;
+            const int ph = (i & 1) * 8 + sub_row;
+            uint2 pk;
+            pk.x = pack_bf16x2(v[i].x, v[i].y);
+            pk.y = pack_bf16x2(v[i].z, v[i].w);
+            *reinterpret_cast<uint2*>(dst + ((c * TS + t) * 16 + ph) * 16 + chunk * 4) = pk;
           }
-        const float var = warp_sum(ss) * (1.0f / (TS * 256 - 1));
-        if (norm_pix) {
-          // HF:598-643 on p = x*std + mean:  (p - mean_p) / (sqrt(var_p) + 1e-6) = (x - mu) * std / (std*sd + 1e-6)
-          mean[c] = mu;
-          inv[c] = kInStd[c] / (kInStd[c] * sqrtf(var) + 1e-6f);
         } else {
-          // HF:644-667: the un-normalised frames themselves, p = x*std + mean
-          mean[c] = -kInMean[c] / kInStd[c];
-          inv[c] = kInStd[c];
-        }
-      }
-      // output order f = ((t*16 + ph)*16 + pw)*3 + c ; lane writes float4 number lane + 32*m
-      float4* dst = reinterpret_cast<float4*>(target + ((long long)b * nm + (s - nv)) * K);
-      const float* tbase = tile + wg * 16;
-#pragma unroll 4
-      for (int m = 0; m < K / 128; ++m) {
-        const int f4 = lane + 32 * m;
-        float o[4];
+          // masked: per-channel statistics over TS*256 pixels, two-pass from registers
+          float mean[3], inv[3];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int f = f4 * 4 + e;
-          const int c = f % 3, pix = f / 3;  // pix = (t*16 + ph)*16 + pw
-          const int pw = pix & 15, ph = (pix >> 4) & 15, t = pix >> 8;
-          const float xv = tbase[(long long)((t * 3 + c) * 16 + ph) * W + pw];
-          const float mu = c == 0 ? mean[0] : (c == 1 ? mean[1] : mean[2]);
-          const float iv = c == 0 ? inv[0] : (c == 1 ? inv[1] : inv[2]);
-          o[e] = (xv - mu) * iv;
+          for (int c = 0; c < 3; ++c) {
+            float sum = 0.f;
+#pragma unroll
+            for (int i = 0; i < NI; ++i)
+              if ((i >> 1) % 3 == c) sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+            const float mu = warp_sum(sum) * (1.0f / (TS * 256));
+            float ss = 0.f;
+#pragma unroll
+            for (int i = 0; i < NI; ++i)
+              if ((i >> 1) % 3 == c) {
+                const float a = v[i].x - mu, bb = v[i].y - mu, cc = v[i].z - mu, dd = v[i].w - mu;
+                ss += (a * a + bb * bb) + (cc * cc + dd * dd);
+              }
+            const float var = warp_sum(ss) * (1.0f / (TS * 256 - 1));
+            if (norm_pix) {
+              // HF:598-643 on p = x*std + mean:  (p - mean_p) / (sqrt(var_p) + 1e-6) = (x - mu) * std / (std*sd + 1e-6)
+              mean[c] = mu;
+              inv[c] = kInStd[c] / (kInStd[c] * sqrtf(var) + 1e-6f);
+            } else {
+              // HF:644-667: the un-normalised frames themselves, p = x*std + mean
+              mean[c] = -kInMean[c] / kInStd[c];
+              inv[c] = kInStd[c];
+            }
+          }
+          // output order f = ((t*16 + ph)*16 + pw)*3 + c: this lane's 4 pixels x 3 channels of (t, ph) are 12
+          // consecutive floats = 3 float4 (16-byte aligned: (.. + chunk*4) * 3 * 4 bytes)
+          float* trow = target + ((long long)b * nm + (s - nv)) * K;
+#pragma unroll
+          for (int t = 0; t < TS; ++t)
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+              const float4 c0 = v[(t * 3 + 0) * 2 + hf], c1 = v[(t * 3 + 1) * 2 + hf], c2 = v[(t * 3 + 2) * 2 + hf];
+              const float m0 = mean[0], m1 = mean[1], m2 = mean[2], i0 = inv[0], i1 = inv[1], i2 = inv[2];
+              const int ph = hf * 8 + sub_row;
+              float4* dst = reinterpret_cast<float4*>(trow + ((t * 16 + ph) * 16 + chunk * 4) * 3);
+              __stcs(dst + 0, make_float4((c0.x - m0) * i0, (c1.x - m1) * i1, (c2.x - m2) * i2, (c0.y - m0) * i0));
+              __stcs(dst + 1, make_float4((c1.y - m1) * i1, (c2.y - m2) * i2, (c0.z - m0) * i0, (c1.z - m1) * i1));
+              __stcs(dst + 2, make_float4((c2.z - m2) * i2, (c0.w - m0) * i0, (c1.w - m1) * i1, (c2.w - m2) * i2));
+            }
         }
-        __stcs(dst + f4, make_float4(o[0], o[1], o[2], o[3]));
       }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[st]);  // this warp has read everything it needs from the stage
     }
   }
 }
@@ -188,38 +220,47 @@ extern "C" int bvc_patchify_target(const float* pixels, const int32_t* slot, int
   const int Tg = T / ts, Hg = H / 16, Wg = W / 16;
   const int N = Tg * Hg * Wg;
   BVC_CHECK_ARG(nv >= 0 && nv <= N);
+  // column split: the widest box (whole tubelets) that keeps a stage <= 48 KB, so several stages fit per SM
+  int split = 1;
+  while (split < Wg && ((size_t)ts * 3 * 16 * (W / split) * 4 > 48 * 1024 || Wg % split != 0)) ++split;
+  BVC_CHECK_ARG(Wg % split == 0);
+  const int BW = W / split;
+  const size_t box_bytes = (size_t)ts * 3 * 16 * BW * 4;
+  int n_stages = (int)((200 * 1024) / box_bytes);
+  if (n_stages > 6) n_stages = 6;
+  BVC_CHECK_ARG(n_stages >= 2);
   CUtensorMap tm;
   const uint64_t dims[5] = {(uint64_t)W, (uint64_t)H, 3, (uint64_t)T, (uint64_t)B};
   const uint64_t strides[4] = {(uint64_t)W * 4, (uint64_t)W * H * 4, (uint64_t)W * H * 3 * 4,
                                (uint64_t)W * H * 3 * T * 4};
-  const uint32_t box[5] = {(uint32_t)W, 16, 3, (uint32_t)ts, 1};
+  const uint32_t box[5] = {(uint32_t)BW, 16, 3, (uint32_t)ts, 1};
   int rc = make_tmap(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, pixels, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE);
   if (rc) return rc;
-  const size_t smem = (size_t)ts * 3 * 16 * W * 4 + 128;
-  int nwarps = (Wg + 1) / 2;
-  if (nwarps > 8) nwarps = 8;
-  if (nwarps < 1) nwarps = 1;
+  const size_t smem = (size_t)n_stages * box_bytes + 2 * n_stages * sizeof(uint64_t) + 128;
   cudaStream_t st = (cudaStream_t)stream;
-  const int grid = B * Tg * Hg;
+  const long long n_items_ll = (long long)B * Tg * Hg * split;
+  BVC_CHECK_ARG(n_items_ll < (1ll << 31));
+  const int n_items = (int)n_items_ll;
+  const int grid = n_items < num_sms() ? n_items : num_sms();  // persistent: one CTA per SM
   static bool attr1 = false, attr2 = false;
   if (ts == 1) {
     if (!attr1) {
-      if (cudaFuncSetAttribute(patchify_target_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024) !=
+      if (cudaFuncSetAttribute(patchify_target_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024) !=
           cudaSuccess)
         return BVC_ERR_LAUNCH;
       attr1 = true;
     }
-    patchify_target_kernel<1><<<grid, nwarps * 32, smem, st>>>(tm, slot, Tg, Hg, Wg, W, nv, N, (bf16*)patches_vis,
-                                                               target, norm_pix);
+    patchify_target_kernel<1><<<grid, kPatchThreads, smem, st>>>(tm, slot, Tg, Hg, Wg, split, n_items, n_stages, nv, N,
+                                                                 (bf16*)patches_vis, target, norm_pix);
   } else {
     if (!attr2) {
-      if (cudaFuncSetAttribute(patchify_target_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024) !=
+      if (cudaFuncSetAttribute(patchify_target_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024) !=
           cudaSuccess)
         return BVC_ERR_LAUNCH;
       attr2 = true;
     }
-    patchify_target_kernel<2><<<grid, nwarps * 32, smem, st>>>(tm, slot, Tg, Hg, Wg, W, nv, N, (bf16*)patches_vis,
-                                                               target, norm_pix);
+    patchify_target_kernel<2><<<grid, kPatchThreads, smem, st>>>(tm, slot, Tg, Hg, Wg, split, n_items, n_stages, nv, N,
+                                                                 (bf16*)patches_vis, target, norm_pix);
   }
   BVC_CHECK_LAUNCH();
   return BVC_OK;

@@ -39,6 +39,18 @@ __device__ long long g_trace[kTraceRoles * kTraceTiles * kTracePoints];
   } while (0)
 #endif
 
+// of every 8 consecutive column pairs, this many take the polynomial exp2 (exp2_poly2: FMA / ALU pipes) instead of
+// MUFU.EX2.  MEASURED NEGATIVE on B200 at these tile shapes (tools/gpu_attn_trace.py, B16 S1568 H6, us per pass):
+//   share   0/8     2/8     3/8     4/8
+//   KV pass 167.1   172.8   181.5   189.8
+//   Q pass  145.7   139.4   147.5   153.7       forward (B64): 438 -> 533 at 3/8
+// the ~5 extra issue slots per element cost what the freed MUFU slots save (2 compute warps per scheduler, issue- and
+// FMA-pipe-bound once the MUFU share drops), so the default is 0; kept for the next restructuring of the softmax warps.
+#ifndef BVC_POLY_NUM
+#define BVC_POLY_NUM 0
+#endif
+constexpr int kPolyNum = BVC_POLY_NUM;
+
 constexpr int kTile = 128;          // rows per Q / KV tile
 constexpr int kTileBytes = 16384;   // 128 x 64 bf16
 constexpr float kLog2e = 1.4426950408889634f;
@@ -274,10 +286,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ o
             for (int i = 0; i < 8; i += 2) {
               const int jj = g * 8 + i;
               const uint64_t x2 = ffma2(pack2(__uint_as_float(sv[c][jj]), __uint_as_float(sv[c][jj + 1])), c2, m2);
-              float a, b;
-              unpack2(x2, a, b);
-              p[i] = exp2f(a);
-              p[i + 1] = exp2f(b);
+              unpack2(((jj >> 1) & 7) < kPolyNum ? exp2_poly2(x2) : exp2_mufu2(x2), p[i], p[i + 1]);
               if (valid < kTile) {  // warp-uniform: last K/V tile only
                 const int col = hh * 64 + c * 32 + jj;
                 if (col >= valid) p[i] = 0.f;
@@ -744,11 +753,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
             // P = exp2((S - lse/scale) * scale * log2e);  dS = P * (dP - delta) * scale
             const uint64_t x2 = MODE_KV ? fmul2(s2, cl2) : ffma2(s2, cl2, nl2);
             const uint64_t y2 = MODE_KV ? fmul2(p2, sc2) : ffma2(p2, sc2, nd2);
-            float a0, a1;
-            unpack2(x2, a0, a1);
-            const float p0 = exp2f(a0), p1 = exp2f(a1);
-            float d0, d1;
-            unpack2(fmul2(pack2(p0, p1), y2), d0, d1);
+            const uint64_t e2 = ((j >> 1) & 7) < kPolyNum ? exp2_poly2(x2) : exp2_mufu2(x2);
+            float p0, p1, d0, d1;
+            unpack2(e2, p0, p1);
+            unpack2(fmul2(e2, y2), d0, d1);
             if (MODE_KV) pk[c * 16 + (j >> 1)] = pack_bf16x2(p0, p1);
             dk[c * 16 + (j >> 1)] = pack_bf16x2(d0, d1);
           }

@@ -100,6 +100,7 @@ extern "C" int bvc_gemm_bf16(const bvc_gemm_args* a, void* stream) {
   BVC_CHECK_ARG(a->act == 0 || a->ld_aux % 8 == 0);
   BVC_CHECK_ARG(a->res == nullptr || a->ldr % 4 == 0);
   BVC_CHECK_ARG(a->target == nullptr || (a->ldt % 4 == 0 && a->loss_partial != nullptr));
+  BVC_CHECK_ARG(a->colsum == nullptr || (a->target == nullptr && a->k_splits == 1 && a->out_seg == 0));
   BVC_CHECK_ARG(a->a_mn_major == 0 ? a->lda >= a->K : a->lda >= a->M);
   BVC_CHECK_ARG(a->b_mn_major == 0 ? a->ldb >= a->K : a->ldb >= a->N);
   cudaStream_t s = (cudaStream_t)stream;

@@ -38,6 +38,7 @@ struct GemmParams {
   long long ldt;
   float* loss_partial;
   bf16* logits_out;
+  float* colsum;
   int has_pre;  // tma_pre describes the epilogue's global operand (residual / target / GELU pre-activation)
 };
 
@@ -343,6 +344,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
           bf16* ob = EPI != EPI_RES ? p.out_bf16 + r0 * p.ldo + col : nullptr;
           float* of = EPI == EPI_RES ? p.out_f32 + r0 * p.ldo + col : nullptr;
           bf16* oa = (EPI == EPI_GELU && p.aux_out) ? p.aux_out + r0 * p.ld_aux + col : nullptr;
+          uint64_t cs01 = 0, cs23 = 0;  // (0.f, 0.f): this lane's column sums over its 8 rows
 #pragma unroll
           for (int it = 0; it < 8; ++it) {
             const int rl = it * 4 + rsub;
@@ -368,6 +370,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
               v01 = fadd2(v01, pack2(pre_f[it].x, pre_f[it].y));
               v23 = fadd2(v23, pack2(pre_f[it].z, pre_f[it].w));
             }
+            if (EPI == EPI_DGELU || EPI == EPI_PLAIN) {
+              cs01 = fadd2(cs01, v01);
+              cs23 = fadd2(cs23, v23);
+            }
             if (EPI == EPI_RES) {
               float x0, x1, x2, x3;
               unpack2(v01, x0, x1);
@@ -380,6 +386,23 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
               pk.y = f32x2_to_bf16x2(v23);
               *reinterpret_cast<uint2*>(ob + (long long)it * 4 * p.ldo) = pk;
             }
+          }
+          if ((EPI == EPI_DGELU || EPI == EPI_PLAIN) && p.colsum) {
+            // fused bias gradient: lanes that share a column group differ in rsub (lane bits 3, 4)
+            float c0, c1, c2, c3;
+            unpack2(cs01, c0, c1);
+            unpack2(cs23, c2, c3);
+#pragma unroll
+            for (int o = 8; o <= 16; o <<= 1) {
+              c0 += __shfl_xor_sync(0xffffffffu, c0, o);
+              c1 += __shfl_xor_sync(0xffffffffu, c1, o);
+              c2 += __shfl_xor_sync(0xffffffffu, c2, o);
+              c3 += __shfl_xor_sync(0xffffffffu, c3, o);
+            }
+            if (rsub == 0)
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p.colsum + col), "f"(c0), "f"(c1),
+                           "f"(c2), "f"(c3)
+                           : "memory");
           }
           __syncwarp();
           continue;
@@ -435,6 +458,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
               }
             }
           }
+          float gcs[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
           for (int it = 0; it < 8; ++it) {
             const int rl = it * 4 + rsub;
@@ -491,7 +515,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
               pk.y = pack_bf16x2(x[2], x[3]);
               *reinterpret_cast<uint2*>(p.out_bf16 + R * p.ldo + col) = pk;
             }
+            gcs[0] += x[0]; gcs[1] += x[1]; gcs[2] += x[2]; gcs[3] += x[3];
           }
+          if (p.colsum && !kSplit && !kLoss)  // per-lane partial sums: a handful of atomics on the ragged edge tiles
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p.colsum + col), "f"(gcs[0]),
+                         "f"(gcs[1]), "f"(gcs[2]), "f"(gcs[3])
+                         : "memory");
         }
         __syncwarp();
       }
@@ -592,6 +621,7 @@ static int launch_gemm(const bvc_gemm_args* a, cudaStream_t stream) {
   p.aux_out = (bf16*)a->aux_out; p.aux_in = (const bf16*)a->aux_in; p.ld_aux = a->ld_aux;
   p.res = a->res; p.ldr = a->ldr; p.res_idx = a->res_idx;
   p.target = a->target; p.ldt = a->ldt; p.loss_partial = a->loss_partial; p.logits_out = (bf16*)a->logits_out;
+  p.colsum = a->colsum;
   if (p.k_splits > 1) {
     BVC_CHECK_ARG(a->out_f32 != nullptr && a->out_bf16 == nullptr && a->bias == nullptr && a->act == 0 &&
                   a->res == nullptr && a->target == nullptr);

@@ -251,7 +251,8 @@ class BlockFn(torch.autograd.Function):
 
         # fc2: x_out = x_mid + act.W2^T + b2
         d_pre = _empty((M, ff), BF16, dev)
-        L.gemm(dxob, w2b, M, ff, d, b_mn=True, ldb=ff, out_bf16=d_pre, act=2, aux_in=pre, ld_aux=ff)
+        # GELU' fused; the epilogue also accumulates the column sums of d_pre = the fc1 bias gradient
+        L.gemm(dxob, w2b, M, ff, d, b_mn=True, ldb=ff, out_bf16=d_pre, act=2, aux_in=pre, ld_aux=ff, colsum=g_b1)
         L.gemm(dxob, act, d, ff, M, a_mn=True, b_mn=True, lda=d, ldb=ff, out_f32=g_w2, k_splits=0)
         if cs_out is not None:
             g_b2 = cs_out
@@ -260,7 +261,6 @@ class BlockFn(torch.autograd.Function):
         del act, pre
         # fc1: pre = u2.W1^T + b1
         L.gemm(d_pre, u2, ff, d, M, a_mn=True, b_mn=True, lda=ff, ldb=d, out_f32=g_w1, k_splits=0)
-        L.colsum(d_pre, M, ff, g_b1)
         d_u2 = _empty((M, d), BF16, dev)
         L.gemm(d_pre, w1b, M, d, ff, b_mn=True, ldb=d, out_bf16=d_u2)
         del d_pre, u2

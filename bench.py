@@ -335,8 +335,17 @@ def run_ours(args):
                             "ms_per_step": kms / args.steps, "share_of_kernel_time": kms / total_kernel_ms,
                             "achieved": ach, "peak": peak, "unit": "TFLOP/s" if tensor else "GB/s", "frac": ach / peak})
         top = dict(kernels[0])
+        # DRAM traffic of the dominant kernel: not measurable live (never under a profiler here) -- taken from the
+        # committed ncu capture of the same command (profiles/README.md), bytes per launch averaged over one step
+        traffic, traffic_src = None, None
+        tpath = os.path.join(ROOT, "profiles", "r01_ncu_gemm_traffic.json")
+        if top["kernel"] == "gemm" and os.path.exists(tpath):
+            with open(tpath) as f:
+                tj = json.load(f)
+            traffic, traffic_src = tj["traffic_bytes_per_launch"], "profiles/r01_ncu_gemm_traffic.json (" + tj["command"] + ")"
         roof = {"bound": top["bound"], "achieved": top["achieved"], "peak": top["peak"], "unit": top["unit"],
-                "frac": top["frac"], "traffic": None, "kernel": top["kernel"],
+                "frac": top["frac"], "traffic": traffic, "traffic_unit": "bytes per launch (dram read + write)",
+                "traffic_source": traffic_src, "kernel": top["kernel"],
                 "peak_source": f"MEASURED_PEAKS.json ({peaks['src']}; sustained bf16 figure: kernel timed inside a long step)",
                 "share_of_step": top["ms_per_step"] / (ms_prof / args.steps),
                 "measured_in": "second timed pass of the same K steps with a CUDA event pair around every libbvc.so "

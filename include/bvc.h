@@ -28,7 +28,7 @@ extern "C" {
 #define BVC_ERR_ARG (-1)
 #define BVC_ERR_DRIVER (-2)
 #define BVC_ERR_LAUNCH (-3)
-#define BVC_ABI_VERSION 5
+#define BVC_ABI_VERSION 6
 
 /* library / build info: returns BVC_ABI_VERSION (bumped when a signature changes) */
 int bvc_abi_version(void);
@@ -79,6 +79,8 @@ int bvc_patchify_target(const float* pixels, const int32_t* slot, int32_t B, int
  *     if res:     v += res[(res_idx ? res_idx[r] : r) * ldr + c]          (fp32 residual / position table)
  *     if target:  (masked MSE, HF:672-673)  if logits_out: logits_out[r*ldo+c] = bf16(v);
  *                 v -= target[r*ldt+c];  tile partial of sum(v*v) -> loss_partial (see bvc_gemm_loss_slots)
+ *     if colsum:  colsum[c] += v  (fp32 atomics; caller zero-fills) -- the bias gradient of the Linear whose output
+ *                 gradient this GEMM produces, without a second pass over it (not with k_splits > 1 / target)
  *     R = segment remap of r with (out_seg, out_seg_stride, out_seg_off)
  *     store:      k_splits > 1 -> atomicAdd(out_f32[R*ldo+c], v)   (caller zero-fills out_f32; no bias/act/res)
  *                 else out_f32[R*ldo+c] = v and/or out_bf16[R*ldo+c] = bf16(v)
@@ -108,6 +110,7 @@ typedef struct bvc_gemm_args {
   int64_t ldt;
   float* loss_partial;    /* fp32 [bvc_gemm_loss_slots(M, N, block_n)], every slot written by the call */
   void* logits_out;       /* bf16, ld = ldo */
+  float* colsum;          /* fp32 [N] or null */
   int32_t block_n;        /* 0 = choose; else 64 / 128 / 192 / 256 */
 } bvc_gemm_args;
 

@@ -5,8 +5,8 @@
 // All operand tiles are 128 rows x 64 bf16 (128-byte rows, 128B swizzle) fetched by one 4-D TMA box; rows past the
 // end of the sequence are zero-filled by TMA, columns past the end are masked in registers.
 //
-// Forward (grid = q-tile x head x clip, 2 CTAs/SM so one CTA's softmax overlaps the other's MMAs):
-//   warp 0 TMA (Q once, K/V ring), warp 1 MMA issuer, warps 2-5 softmax (one query row per thread).
+// Forward (persistent, one CTA per SM over (q-tile pair, head, clip) items; see the kernel):
+//   warp 0 TMA loads, warp 1 MMA issuer, warp 3 TMA stores, warps 4-7 / 8-11 softmax of the pair's two query tiles.
 //   S = Q K^T -> TMEM (128 cols); softmax threads read S, exp2 with a lazily updated running max (rescale O in TMEM
 //   only when the max grows by > 8 in log2 units), write P (bf16, packed) back into TMEM as the A operand of
 //   O += P V (tcgen05.mma with A from TMEM): P never touches shared memory, whose bandwidth (128 B/clk/SM, shared
@@ -89,257 +89,338 @@ __device__ __forceinline__ uint32_t ptile_chunk_off(int row, int chunk16 /*0..15
 }
 
 // ================================================================================================ forward
-constexpr int kFwdThreads = 192;
-constexpr int kFwdSmem = kTileBytes * (1 + 2 + 2) + 128;  // Q, K[2], V[2], barriers
+// PERSISTENT, two query tiles in flight per CTA (one CTA per SM walks (query-tile PAIR, head, clip) work items):
+//   warpgroup 0: warp 0 TMA loads (the pair's two Q tiles, double-buffered across items; K/V ring shared by both
+//                tiles), warp 1 MMA issue, warp 3 TMA stores
+//   warps 4-7  : softmax of query tile 0 of the pair,  warps 8-11: softmax of query tile 1
+//                (thread = one query row x all 128 key columns of the K/V tile; TMEM lane quadrant = warp % 4)
+// The two softmax groups are independent pipelines (own S, O, P TMEM regions and barriers) that share the tensor
+// pipe and the K/V tiles in shared memory: while one group is in its MUFU-bound exponentials the other loads scores /
+// stores probabilities, which is what keeps the MUFU pipe (the bound at head_dim 64: 1024 clk per 128x128 tile) busy.
+// TMEM (512 columns): S0, S1 (128 each), O0, O1 (64 each), packed-bf16 P0, P1 (64 each; A operand of O += P V straight
+// from TMEM: P never touches shared memory).  The running maximum is updated lazily (O is rescaled in TMEM only when
+// the maximum grows by > 8 in log2 units).  O leaves through the finished item's Q buffers (128B-swizzled) and one
+// TMA store per tile, which also clips the rows past the end of the sequence.
+constexpr int kFwdThreads = 384;
+constexpr int kFwdStages = 4;
+constexpr int kFwdRegsCtl = 88, kFwdRegsCompute = 208;  // setmaxnreg split, as in the backward kernel
+constexpr int kFwdSmem = kTileBytes * (4 + 2 * kFwdStages) + 256;
 
-__global__ void __launch_bounds__(kFwdThreads, 2)
-attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ out, float* __restrict__ lse, int S,
-                int H, float scale_log2) {
+__global__ void __launch_bounds__(kFwdThreads, 1)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_out,
+                float* __restrict__ lse, int S, int H, int n_work, float scale_log2) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* sQ = smem;
-  uint8_t* sK = smem + kTileBytes;          // 2 stages
-  uint8_t* sV = smem + 3 * kTileBytes;      // 2 stages
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 5 * kTileBytes);
-  uint64_t* q_full = bars + 0;
-  uint64_t* k_full = bars + 1;    // [2]   K and V have separate rings: a K stage is released as soon as its
-  uint64_t* k_empty = bars + 3;   // [2]   S = Q K^T MMA has run (long before the P V MMA of the same tile), which
-  uint64_t* v_full = bars + 5;    // [2]   gives the next K tile's TMA two softmax periods of lead time
-  uint64_t* v_empty = bars + 7;   // [2]
-  uint64_t* s_full = bars + 9;
-  uint64_t* s_free = bars + 10;
-  uint64_t* p_full = bars + 11;
-  uint64_t* o_full = bars + 12;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+  uint8_t* sQ = smem;                                    // [2 item buffers][2 tiles of the pair]
+  uint8_t* sK = smem + 4 * kTileBytes;                   // [stages]
+  uint8_t* sV = smem + (4 + kFwdStages) * kTileBytes;    // [stages]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (4 + 2 * kFwdStages) * kTileBytes);
+  uint64_t* q_full = bars + 0;                    // [2]
+  uint64_t* q_empty = bars + 2;                   // [2]
+  uint64_t* kv_full = bars + 4;                   // [stages]
+  uint64_t* kv_empty = bars + 4 + kFwdStages;     // [stages]
+  uint64_t* s_full = bars + 4 + 2 * kFwdStages;   // [2 groups]
+  uint64_t* s_free = s_full + 2;                  // [2]
+  uint64_t* p_full = s_full + 4;                  // [2]
+  uint64_t* p_free = s_full + 6;                  // [2]  P V MMA of the group's tile complete (P reusable, O updated)
+  uint64_t* epi_full = s_full + 8;
+  uint64_t* o_free = s_full + 9;                  // [2] softmax group -> MMA warp: the item's O has been read
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 11);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * kTile, h = blockIdx.y, b = blockIdx.z;
-  const int n_kv = (S + kTile - 1) / kTile;
+  const int n_kv = (S + kTile - 1) / kTile;       // K/V tiles per sequence
+  const int n_pairs = (n_kv + 1) / 2;             // query-tile pairs per (clip, head)
+  const int n_my = (n_work - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int n_glob = n_my * n_kv;
+  auto item_pair = [&](int k) { return ((int)blockIdx.x + k * (int)gridDim.x) % n_pairs; };
+  auto item_bh = [&](int k) { return ((int)blockIdx.x + k * (int)gridDim.x) / n_pairs; };  // = b * H + h
 
   if (threadIdx.x == 0) {
     if ((smem_u32(smem) & 1023u) != 0) __trap();
     tma_prefetch_desc(&tm_qkv);
-    mbar_init(q_full, 1);
+    tma_prefetch_desc(&tm_out);
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&k_full[i], 1);
-      mbar_init(&k_empty[i], 1);
-      mbar_init(&v_full[i], 1);
-      mbar_init(&v_empty[i], 1);
+      mbar_init(&q_full[i], 1);
+      mbar_init(&q_empty[i], 1);
+      mbar_init(&s_full[i], 1);
+      mbar_init(&s_free[i], 4);
+      mbar_init(&p_full[i], 4);
+      mbar_init(&p_free[i], 1);
     }
-    mbar_init(s_full, 1);
-    mbar_init(s_free, 4);
-    mbar_init(p_full, 4);
-    mbar_init(o_full, 1);
+    for (int i = 0; i < kFwdStages; ++i) {
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+    }
+    mbar_init(epi_full, 8);
+    mbar_init(&o_free[0], 4);
+    mbar_init(&o_free[1], 4);
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, 256);
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tS = tmem_base, tO = tmem_base + 128, tP = tmem_base + 192;  // P: [128][128] bf16 = 64 columns
+  // group t (query tile t of the pair): S at 128 t, O at 256 + 64 t, P at 384 + 64 t
+  const uint32_t tS = tmem_base, tO = tmem_base + 256, tP = tmem_base + 384;
 
-  if (warp == 0) {
-    if (lane == 0) {
-      mbar_expect_tx(q_full, kTileBytes);
-      tma_load_4d(sQ, &tm_qkv, q_full, 0, h, q0, b);
-      for (int j = 0; j < n_kv; ++j) {
-        const int st = j & 1;
-        const uint32_t par = ((uint32_t)(j >> 1) & 1u) ^ 1u;
-        mbar_wait(&k_empty[st], par);
-        mbar_expect_tx(&k_full[st], kTileBytes);
-        tma_load_4d(sK + st * kTileBytes, &tm_qkv, &k_full[st], 0, H + h, j * kTile, b);
-        mbar_wait(&v_empty[st], par);
-        mbar_expect_tx(&v_full[st], kTileBytes);
-        tma_load_4d(sV + st * kTileBytes, &tm_qkv, &v_full[st], 0, 2 * H + h, j * kTile, b);
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kFwdRegsCtl));
+    if (warp == 0) {
+      if (lane == 0) {
+        int g = 0;
+        for (int k = 0; k < n_my; ++k) {
+          const int q0 = item_pair(k) * 2 * kTile, bh = item_bh(k), h = bh % H, b = bh / H;
+          uint8_t* qb = sQ + (k & 1) * 2 * kTileBytes;
+          mbar_wait(&q_empty[k & 1], ((uint32_t)(k >> 1) & 1u) ^ 1u);
+          mbar_expect_tx(&q_full[k & 1], 2 * kTileBytes);
+          tma_load_4d(qb, &tm_qkv, &q_full[k & 1], 0, h, q0, b);
+          tma_load_4d(qb + kTileBytes, &tm_qkv, &q_full[k & 1], 0, h, q0 + kTile, b);  // may be entirely past S: zero fill
+          for (int j = 0; j < n_kv; ++j, ++g) {
+            const int st = g % kFwdStages;
+            mbar_wait(&kv_empty[st], ((uint32_t)(g / kFwdStages) & 1u) ^ 1u);
+            mbar_expect_tx(&kv_full[st], 2 * kTileBytes);
+            tma_load_4d(sK + st * kTileBytes, &tm_qkv, &kv_full[st], 0, H + h, j * kTile, b);
+            tma_load_4d(sV + st * kTileBytes, &tm_qkv, &kv_full[st], 0, 2 * H + h, j * kTile, b);
+          }
+        }
       }
-    }
-  } else if (warp == 1) {
-    // MMA issuer: warp-uniform control flow, one elected lane issues (see elect_one in bvc_ptx.cuh)
-    constexpr uint32_t idesc_o = umma_idesc_bf16(64, 0, 1, 128);
-    const uint64_t dQ = desc_k(smem_u32(sQ), 0);
-    // the last K/V tile of a sequence is ragged (1568 = 12 x 128 + 32; 160 = 128 + 32): size its MMAs to the valid
-    // rows rounded up to 16 (N of S = Q K^T, K-steps of O += P V) instead of paying for a full 128
-    auto n_valid16 = [&](int j) { return min(kTile, (S - j * kTile + 15) & ~15); };
-    mbar_wait(q_full, 0);
-    mbar_wait(&k_full[0], 0);
-    tc_fence_after();
-    if (elect_one()) {
-      const uint64_t dK = desc_k(smem_u32(sK), 0);
-      const uint32_t idesc_s = umma_idesc_bf16(n_valid16(0), 0, 0, 128);
+    } else if (warp == 1) {
+      // MMA issuer: warp-uniform control flow, one elected lane issues (see elect_one in bvc_ptx.cuh).  Flat loop over
+      // the CTA's K/V tiles g (item k = g / n_kv, tile j = g % n_kv); per tile, for both groups: S of tile g + 1, then
+      // P V of tile g.
+      constexpr uint32_t idesc_o = umma_idesc_bf16(64, 0, 1, 128);
+      // the last K/V tile of a sequence is ragged (1568 = 12 x 128 + 32; 160 = 128 + 32): size its MMAs to the valid
+      // rows rounded up to 16 (N of S = Q K^T, K-steps of O += P V) instead of paying for a full 128
+      auto valid16 = [&](int j) { return min(kTile, (S - j * kTile + 15) & ~15); };
+      auto issue_s = [&](int k, int j, int st, int t) {
+        const uint64_t dQ = desc_k(smem_u32(sQ + ((k & 1) * 2 + t) * kTileBytes), 0);
+        const uint64_t dK = desc_k(smem_u32(sK + st * kTileBytes), 0);
+        const uint32_t idesc_s = umma_idesc_bf16(valid16(j), 0, 0, 128);
+        const uint32_t d = tS + (uint32_t)t * 128;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) umma_bf16_ss(tS, dQ + 2 * k, dK + 2 * k, idesc_s, k > 0);
-      umma_commit(s_full);
-      umma_commit(&k_empty[0]);
-    }
-    __syncwarp();
-    for (int j = 0; j < n_kv; ++j) {
-      if (j + 1 < n_kv) {
-        const int st = (j + 1) & 1;
-        mbar_wait(&k_full[st], (uint32_t)((j + 1) >> 1) & 1u);
-        mbar_wait(s_free, (uint32_t)j & 1u);
+        for (int kk = 0; kk < 4; ++kk) umma_bf16_ss(d, dQ + 2 * kk, dK + 2 * kk, idesc_s, kk > 0);
+        umma_commit(&s_full[t]);
+      };
+      if (n_glob > 0) {
+        mbar_wait(&q_full[0], 0);
+        mbar_wait(&kv_full[0], 0);
         tc_fence_after();
         if (elect_one()) {
-          const uint64_t dK = desc_k(smem_u32(sK + st * kTileBytes), 0);
-          const uint32_t idesc_s = umma_idesc_bf16(n_valid16(j + 1), 0, 0, 128);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) umma_bf16_ss(tS, dQ + 2 * k, dK + 2 * k, idesc_s, k > 0);
-          umma_commit(s_full);
-          umma_commit(&k_empty[st]);
+          issue_s(0, 0, 0, 0);
+          issue_s(0, 0, 0, 1);
         }
         __syncwarp();
       }
-      mbar_wait(&v_full[j & 1], (uint32_t)(j >> 1) & 1u);
-      mbar_wait(p_full, (uint32_t)j & 1u);
-      tc_fence_after();
-      const int ksteps = n_valid16(j) >> 4;
-      if (elect_one()) {
-        // O += P V : A = P (TMEM, packed bf16, 8 columns per K = 16 step), B = V_j (MN-major: n = d, k = kv)
-        const uint64_t dV = desc_mn(smem_u32(sV + (j & 1) * kTileBytes), 0, 8192);
+      auto issue_pv = [&](int j, int cst, int t) {
+        // O_t += P_t V : A = P (TMEM, packed bf16, 8 columns per K = 16 step), B = V_j (MN-major: n = d, k = kv)
+        const int ksteps = valid16(j) >> 4;
+        const uint64_t dV = desc_mn(smem_u32(sV + cst * kTileBytes), 0, 8192);
+        const uint32_t aP = tP + (uint32_t)t * 64, dO = tO + (uint32_t)t * 64;
         const uint32_t acc0 = j > 0;
         if (ksteps == 8) {
 #pragma unroll
-          for (int k = 0; k < 8; ++k) umma_bf16_ts(tO, tP + k * 8, dV + 128 * k, idesc_o, acc0 | (k > 0));
+          for (int kk = 0; kk < 8; ++kk) umma_bf16_ts(dO, aP + kk * 8, dV + 128 * kk, idesc_o, acc0 | (kk > 0));
         } else {
-          for (int k = 0; k < ksteps; ++k) umma_bf16_ts(tO, tP + k * 8, dV + 128 * k, idesc_o, acc0 | (k > 0));
+          for (int kk = 0; kk < ksteps; ++kk) umma_bf16_ts(dO, aP + kk * 8, dV + 128 * kk, idesc_o, acc0 | (kk > 0));
         }
-        umma_commit(o_full);
-        umma_commit(&v_empty[j & 1]);
+        umma_commit(&p_free[t]);
+        if (t == 1) umma_commit(&kv_empty[cst]);  // group 1's P V is the last reader of the stage
+      };
+      // Issue order per K/V tile g: S0(g+1), PV0(g), S1(g+1), PV1(g).  (The rotated order S0, PV1(g-1), S1, PV0 -- the
+      // arrival order of the events when the groups run half a tile out of phase -- measured 8 % slower.)
+      int k = 0, j = 0;
+      for (int g = 0; g < n_glob; ++g) {
+        int k1 = k, j1 = j + 1;
+        if (j1 == n_kv) {
+          j1 = 0;
+          ++k1;
+        }
+        const int st1 = (g + 1) % kFwdStages, cst = g % kFwdStages;
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          if (g + 1 < n_glob) {
+            if (t == 0) {
+              if (j1 == 0) mbar_wait(&q_full[k1 & 1], (uint32_t)(k1 >> 1) & 1u);
+              mbar_wait(&kv_full[st1], (uint32_t)((g + 1) / kFwdStages) & 1u);
+            }
+            mbar_wait(&s_free[t], (uint32_t)g & 1u);  // group t has its scores of tile g in registers
+            tc_fence_after();
+            if (elect_one()) issue_s(k1, j1, st1, t);
+            __syncwarp();
+          }
+          mbar_wait(&p_full[t], (uint32_t)g & 1u);
+          // a new item's first P V overwrites O: the group's epilogue must have read the previous item's O
+          if (j == 0 && k > 0) mbar_wait(&o_free[t], (uint32_t)(k - 1) & 1u);
+          tc_fence_after();
+          if (elect_one()) issue_pv(j, cst, t);
+          __syncwarp();
+        }
+        k = k1;
+        j = j1;
       }
-      __syncwarp();
+    } else if (warp == 3) {
+      // store warp: one TMA store per staged O tile, then the item's Q buffers go back to the TMA warp
+      for (int k = 0; k < n_my; ++k) {
+        const int q0 = item_pair(k) * 2 * kTile, bh = item_bh(k), h = bh % H, b = bh / H;
+        uint8_t* qb = sQ + (k & 1) * 2 * kTileBytes;
+        mbar_wait(epi_full, (uint32_t)k & 1u);
+        if (lane == 0) {
+          tma_store_4d(&tm_out, qb, 0, h, q0, b);
+          if (q0 + kTile < S) tma_store_4d(&tm_out, qb + kTileBytes, 0, h, q0 + kTile, b);
+          tma_store_commit();
+          tma_store_wait_read0();
+          mbar_arrive(&q_empty[k & 1]);
+        }
+        __syncwarp();
+      }
+      if (lane == 0) tma_store_wait0();
     }
   } else {
-    const int q = warp & 3;
-    const int row = q * 32 + lane;
-    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
-    float m_used = -INFINITY, l = 0.f;
-    for (int j = 0; j < n_kv; ++j) {
-      mbar_wait(s_full, (uint32_t)j & 1u);
-      tc_fence_after();
-      const int valid = S - j * kTile;  // columns >= valid are past the end of the sequence
-      // pass 1: row maximum of the raw scores, two 32-column chunks of S in registers at a time (keeping all 128
-      // scores live spilled ~340 B per thread at the 168-register cap that 2 CTAs/SM imposes)
-      float mx = -INFINITY;
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kFwdRegsCompute));
+    const int q4 = warp & 3;
+    const int t = (warp - 4) >> 2;  // which query tile of the pair this group owns
+    const int row = q4 * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(q4 * 32) << 16;
+    const uint32_t mS = tS + (uint32_t)t * 128 + lane_base, mO = tO + (uint32_t)t * 64 + lane_base;
+    const uint32_t mP = tP + (uint32_t)t * 64 + lane_base;
+    const uint64_t c2 = pack2(scale_log2, scale_log2);
+    int g = 0;
+    for (int k = 0; k < n_my; ++k) {
+      const int q0 = (item_pair(k) * 2 + t) * kTile, bh = item_bh(k);
+      float m_used = -INFINITY, l = 0.f;
+      for (int j = 0; j < n_kv; ++j, ++g) {
+        const int valid = S - j * kTile;  // columns >= valid are past the end of the sequence (ragged last tile)
+        const bool tr = lane == 0 && q4 == 0;
+        if (tr) BVC_TR(t, g, 0);
+        mbar_wait(&s_full[t], (uint32_t)g & 1u);
+        if (tr) BVC_TR(t, g, 1);
+        tc_fence_after();
+        uint32_t sv[4][32];  // the whole score row of this tile
 #pragma unroll
-      for (int hh = 0; hh < 2; ++hh) {
-        uint32_t sv[2][32];
-        tmem_ld_32x32b_x32(tS + lane_base + hh * 64, sv[0]);
-        tmem_ld_32x32b_x32(tS + lane_base + hh * 64 + 32, sv[1]);
-        tmem_ld_wait();
+        for (int c = 0; c < 4; ++c) tmem_ld_32x32b_x32(mS + c * 32, sv[c]);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) tmem_ld_wait_pin(sv[c]);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_free[t]);  // the MMA warp may overwrite S with the next tile's scores
+        if (tr) BVC_TR(t, g, 2);
+        float mx = -INFINITY;
         if (valid >= kTile) {
+          float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};  // independent chains
 #pragma unroll
-          for (int c = 0; c < 2; ++c)
+          for (int c = 0; c < 4; ++c)
 #pragma unroll
-            for (int i = 0; i < 32; i += 2) mx = fmax3(mx, __uint_as_float(sv[c][i]), __uint_as_float(sv[c][i + 1]));
+            for (int i = 0; i < 32; ++i) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(sv[c][i]));
+          mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
         } else {
 #pragma unroll
-          for (int c = 0; c < 2; ++c)
+          for (int c = 0; c < 4; ++c)
 #pragma unroll
             for (int i = 0; i < 32; ++i)
-              if (hh * 64 + c * 32 + i < valid) mx = fmaxf(mx, __uint_as_float(sv[c][i]));
+              if (c * 32 + i < valid) mx = fmaxf(mx, __uint_as_float(sv[c][i]));
         }
-      }
-      mx *= scale_log2;  // raw scores -> log2 domain (scale_log2 > 0)
-      const bool need = mx > m_used + 8.0f;
-      float alpha = 1.0f;
-      if (need) {
-        alpha = exp2f(m_used - mx);  // 0 on the first tile
-        m_used = mx;
-      }
-      if (j > 0) {
-        mbar_wait(o_full, (uint32_t)(j - 1) & 1u);  // PV_{j-1} done: P smem reusable, O stable
-        tc_fence_after();
-        if (__any_sync(0xffffffffu, need)) {
-#pragma unroll
-          for (int c = 0; c < 2; ++c) {
-            uint32_t ov[32];
-            tmem_ld_32x32b_x32(tO + lane_base + c * 32, ov);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * alpha);
-            tmem_st_32x32b_x32(tO + lane_base + c * 32, ov);
-          }
-          tmem_st_wait();
+        mx *= scale_log2;  // raw scores -> log2 domain (scale_log2 > 0)
+        const bool need = mx > m_used + 8.0f;
+        float alpha = 1.0f;
+        if (need) {
+          alpha = exp2f(m_used - mx);  // 0 on the first tile
+          m_used = mx;
         }
-      }
-      l *= alpha;
-      // pass 2: P = exp2(S * scale_log2 - m), row sum, bf16 P into the swizzled A-operand tile
-      const uint64_t c2 = pack2(scale_log2, scale_log2), m2 = pack2(-m_used, -m_used);
-      uint64_t lsum2 = pack2(0.f, 0.f);
+        if (j > 0) {
+          // P V of the previous tile: P is reusable and O is up to date (needed for the rescale)
+          mbar_wait(&p_free[t], (uint32_t)(g - 1) & 1u);
+          tc_fence_after();
+          if (__any_sync(0xffffffffu, need)) {
 #pragma unroll
-      for (int hh = 0; hh < 2; ++hh) {
-        uint32_t sv[2][32];
-        tmem_ld_32x32b_x32(tS + lane_base + hh * 64, sv[0]);
-        tmem_ld_32x32b_x32(tS + lane_base + hh * 64 + 32, sv[1]);
-        tmem_ld_wait();
-        if (hh == 1) {  // S fully consumed: the MMA warp may overwrite it with the next tile's scores
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(s_free);
-        }
-        uint32_t pk[32];  // this thread's 64 probabilities of the half-row, packed bf16x2
+            for (int c = 0; c < 2; ++c) {
+              uint32_t ov[32];
+              tmem_ld_32x32b_x32(mO + c * 32, ov);
+              tmem_ld_wait();
 #pragma unroll
-        for (int c = 0; c < 2; ++c)
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            float p[8];
-#pragma unroll
-            for (int i = 0; i < 8; i += 2) {
-              const int jj = g * 8 + i;
-              const uint64_t x2 = ffma2(pack2(__uint_as_float(sv[c][jj]), __uint_as_float(sv[c][jj + 1])), c2, m2);
-              unpack2(((jj >> 1) & 7) < kPolyNum ? exp2_poly2(x2) : exp2_mufu2(x2), p[i], p[i + 1]);
-              if (valid < kTile) {  // warp-uniform: last K/V tile only
-                const int col = hh * 64 + c * 32 + jj;
-                if (col >= valid) p[i] = 0.f;
-                if (col + 1 >= valid) p[i + 1] = 0.f;
-              }
-              lsum2 = fadd2(lsum2, pack2(p[i], p[i + 1]));
+              for (int i = 0; i < 32; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * alpha);
+              tmem_st_32x32b_x32(mO + c * 32, ov);
             }
-            pk[c * 16 + g * 4 + 0] = pack_bf16x2(p[0], p[1]);
-            pk[c * 16 + g * 4 + 1] = pack_bf16x2(p[2], p[3]);
-            pk[c * 16 + g * 4 + 2] = pack_bf16x2(p[4], p[5]);
-            pk[c * 16 + g * 4 + 3] = pack_bf16x2(p[6], p[7]);
           }
-        tmem_st_32x32b_x32(tP + lane_base + hh * 32, pk);
+        }
+        l *= alpha;
+        if (tr) BVC_TR(t, g, 3);
+        // P = exp2(S * scale_log2 - m), row sum, packed bf16 P back into TMEM (32 columns of P per 64 scores)
+        const uint64_t m2 = pack2(-m_used, -m_used);
+        uint64_t lsum2 = pack2(0.f, 0.f);
+        auto softmax_row = [&](auto tail_tag) {
+          constexpr bool kTail = decltype(tail_tag)::value;
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            uint32_t pk[32];
+#pragma unroll
+            for (int c = 0; c < 2; ++c)
+#pragma unroll
+              for (int i = 0; i < 32; i += 2) {
+                const uint32_t(&s32)[32] = sv[hh * 2 + c];
+                const uint64_t x2 = ffma2(pack2(__uint_as_float(s32[i]), __uint_as_float(s32[i + 1])), c2, m2);
+                float p0, p1;
+                unpack2(exp2_mufu2(x2), p0, p1);
+                if (kTail) {
+                  const int col = hh * 64 + c * 32 + i;
+                  if (col >= valid) p0 = 0.f;
+                  if (col + 1 >= valid) p1 = 0.f;
+                }
+                lsum2 = fadd2(lsum2, pack2(p0, p1));
+                pk[c * 16 + (i >> 1)] = pack_bf16x2(p0, p1);
+              }
+            tmem_st_32x32b_x32(mP + hh * 32, pk);
+          }
+        };
+        if (valid >= kTile) softmax_row(std::false_type{});
+        else softmax_row(std::true_type{});
+        float ls0, ls1;
+        unpack2(lsum2, ls0, ls1);
+        l += ls0 + ls1;
+        if (tr) BVC_TR(t, g, 4);
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[t]);
+        if (tr) BVC_TR(t, g, 5);
       }
-      float lsum, lsum_hi;
-      unpack2(lsum2, lsum, lsum_hi);
-      lsum += lsum_hi;
-      l += lsum;
-      tmem_st_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(p_full);
-    }
-    mbar_wait(o_full, (uint32_t)(n_kv - 1) & 1u);
-    tc_fence_after();
-    const float inv_l = 1.0f / l;
-    const int qrow = q0 + row;
-    bf16* orow = out + ((long long)(b * (long long)S + qrow) * H + h) * 64;
+      // item epilogue: O / l -> bf16 -> this group's Q buffer of the item (128B-swizzled) -> TMA store (store warp)
+      mbar_wait(&p_free[t], (uint32_t)(g - 1) & 1u);  // the item's last P V
+      if (lane == 0 && q4 == 0) BVC_TR(t, g - 1, 6);
+      tc_fence_after();
+      const float inv_l = 1.0f / l;
+      uint8_t* stage = sQ + ((k & 1) * 2 + t) * kTileBytes;
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      uint32_t ov[32];
-      tmem_ld_32x32b_x32(tO + lane_base + c * 32, ov);
-      tmem_ld_wait();
-      if (qrow < S) {
+      for (int c = 0; c < 2; ++c) {
+        uint32_t ov[32];
+        tmem_ld_32x32b_x32(mO + c * 32, ov);
+        tmem_ld_wait();
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          uint4 pk;
-          pk.x = pack_bf16x2(__uint_as_float(ov[g * 8 + 0]) * inv_l, __uint_as_float(ov[g * 8 + 1]) * inv_l);
-          pk.y = pack_bf16x2(__uint_as_float(ov[g * 8 + 2]) * inv_l, __uint_as_float(ov[g * 8 + 3]) * inv_l);
-          pk.z = pack_bf16x2(__uint_as_float(ov[g * 8 + 4]) * inv_l, __uint_as_float(ov[g * 8 + 5]) * inv_l);
-          pk.w = pack_bf16x2(__uint_as_float(ov[g * 8 + 6]) * inv_l, __uint_as_float(ov[g * 8 + 7]) * inv_l);
-          *reinterpret_cast<uint4*>(orow + c * 32 + g * 8) = pk;
+        for (int gq = 0; gq < 4; ++gq) {
+          uint4 o4;
+          o4.x = pack_bf16x2(__uint_as_float(ov[gq * 8 + 0]) * inv_l, __uint_as_float(ov[gq * 8 + 1]) * inv_l);
+          o4.y = pack_bf16x2(__uint_as_float(ov[gq * 8 + 2]) * inv_l, __uint_as_float(ov[gq * 8 + 3]) * inv_l);
+          o4.z = pack_bf16x2(__uint_as_float(ov[gq * 8 + 4]) * inv_l, __uint_as_float(ov[gq * 8 + 5]) * inv_l);
+          o4.w = pack_bf16x2(__uint_as_float(ov[gq * 8 + 6]) * inv_l, __uint_as_float(ov[gq * 8 + 7]) * inv_l);
+          *reinterpret_cast<uint4*>(stage + row * 128 + (((c * 4 + gq) ^ (row & 7)) << 4)) = o4;
         }
       }
+      if (q0 + row < S) lse[(long long)bh * S + q0 + row] = (m_used + log2f(l)) * 0.6931471805599453f;
+      tc_fence_before();
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&o_free[t]);
+        mbar_arrive(epi_full);
+      }
+      if (lane == 0 && q4 == 0) BVC_TR(t, g - 1, 7);
     }
-    if (qrow < S) lse[((long long)b * H + h) * S + qrow] = (m_used + log2f(l)) * 0.6931471805599453f;
   }
 
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 256);
+    tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -840,11 +921,16 @@ extern "C" int bvc_attn_fwd(const void* qkv, int32_t B, int32_t S, int32_t H, fl
       return BVC_ERR_LAUNCH;
     attr_done = true;
   }
-  CUtensorMap tm;
+  CUtensorMap tm, to;
   int rc = make_head_tmap(&tm, qkv, 3 * H, S, B);
   if (rc) return rc;
-  dim3 grid((S + kTile - 1) / kTile, H, B);
-  attn_fwd_kernel<<<grid, kFwdThreads, kFwdSmem, (cudaStream_t)stream>>>(tm, (bf16*)out, lse, S, H, scale * kLog2e);
+  rc = make_head_tmap(&to, out, H, S, B);
+  if (rc) return rc;
+  const int n_kv = (S + kTile - 1) / kTile;
+  const long long n_work = (long long)((n_kv + 1) / 2) * H * B;  // (query-tile pair, head, clip)
+  BVC_CHECK_ARG(n_work < (1ll << 30));
+  const int grid = (int)(n_work < num_sms() ? n_work : num_sms());  // persistent: one CTA per SM
+  attn_fwd_kernel<<<grid, kFwdThreads, kFwdSmem, (cudaStream_t)stream>>>(tm, to, lse, S, H, (int)n_work, scale * kLog2e);
   BVC_CHECK_LAUNCH();
   return BVC_OK;
 }
@@ -889,6 +975,10 @@ extern "C" int bvc_attn_bwd(const void* qkv, const void* out, const void* dout, 
 extern "C" int bvc_debug_trace_copy(long long* dst_host, int n) {
   if (n > kTraceRoles * kTraceTiles * kTracePoints) n = kTraceRoles * kTraceTiles * kTracePoints;
   return (int)cudaMemcpyFromSymbol(dst_host, g_trace, sizeof(long long) * n);
+}
+extern "C" int bvc_debug_attn_fwd(const void* qkv, int32_t B, int32_t S, int32_t H, float scale, void* out, float* lse,
+                                  void* stream) {
+  return bvc_attn_fwd(qkv, B, S, H, scale, out, lse, stream);
 }
 extern "C" int bvc_debug_attn_bwd_pass(const void* qkv, const void* dout, const float* lse, const float* delta,
                                        int32_t B, int32_t S, int32_t H, float scale, void* dqkv, int32_t mode_kv,

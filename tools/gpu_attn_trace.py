@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""Per-phase SM-clock trace of the backward attention pipeline (CTA 0): builds csrc/attn.cu with -DBVC_TRACE into
+"""Per-phase SM-clock trace of the attention pipelines (CTA 0; mode 1 = backward KV pass, 0 = backward Q pass,
+2 = forward: columns are wait S | LDTM | max + rescale | exp + pack | STTM for softmax group 0): builds csrc/attn.cu with -DBVC_TRACE into
 libbvc_trace.so (done on the build box: `nvcc ... -DBVC_TRACE -shared csrc/attn.cu -o libbvc_trace.so`), runs one
 pass and prints, per streamed tile, how long each role spent in each phase.
     python tools/gpu_attn_trace.py B S H mode_kv
@@ -22,15 +23,28 @@ lse = torch.randn(B, H, S, device=dev) + 5
 delta = torch.randn(B, H, S, device=dev)
 dqkv = torch.zeros_like(qkv)
 P = lambda t: C.c_void_p(t.data_ptr())
+out = torch.zeros(B, S, d, device=dev, dtype=torch.bfloat16)
+
+
+def run_pass():
+    if mode == 2:  # forward
+        return lib.bvc_debug_attn_fwd(P(qkv), B, S, H, C.c_float(0.125), P(out), P(lse), None)
+    return lib.bvc_debug_attn_bwd_pass(P(qkv), P(do), P(lse), P(delta), B, S, H, C.c_float(0.125), P(dqkv), mode, None)
+
+
 for _ in range(3):
-    rc = lib.bvc_debug_attn_bwd_pass(P(qkv), P(do), P(lse), P(delta), B, S, H, C.c_float(0.125), P(dqkv), mode, None)
+    rc = run_pass()
     assert rc == 0, rc
 torch.cuda.synchronize()
 s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 s.record()
-lib.bvc_debug_attn_bwd_pass(P(qkv), P(do), P(lse), P(delta), B, S, H, C.c_float(0.125), P(dqkv), mode, None)
+run_pass()
 e.record()
 torch.cuda.synchronize()
+if False:
+  for _ in range(3):
+    rc = lib.bvc_debug_attn_bwd_pass(P(qkv), P(do), P(lse), P(delta), B, S, H, C.c_float(0.125), P(dqkv), mode, None)
+    assert rc == 0, rc
 print(f"TRACE pass mode_kv={mode} B{B} S{S} H{H}: {s.elapsed_time(e)*1e3:.1f} us")
 R, T, K = 3, 256, 8
 buf = np.zeros(R * T * K, dtype=np.int64)
@@ -38,6 +52,8 @@ lib.bvc_debug_trace_copy(buf.ctypes.data_as(C.POINTER(C.c_longlong)), buf.size)
 tr = buf.reshape(R, T, K)
 n_it = (S + 127) // 128
 n_items = (((S + 127) // 128) * H * B + 147) // 148
+if mode == 2:
+    n_items = ((((S + 127) // 128 + 1) // 2) * H * B + 147) // 148
 G = min(T, n_it * n_items)
 t0 = tr[0, 0, 0]
 print("TRACE compute warp (half 0): per tile: wait_sdp | ldtm | math | wait_pds_free | sttm ; [epilogue wait | store]")

@@ -114,6 +114,20 @@ __device__ __forceinline__ uint64_t gelu_erf_grad2(uint64_t x2) {
   const uint64_t pdf2 = fmul2(pack2(exp2f(e0), exp2f(e1)), pack2(0.3989422804014327f, 0.3989422804014327f));
   return ffma2(x2, pdf2, cdf2);
 }
+// gelu(x) and gelu'(x) from one evaluation of Phi(-|x|) (the forward epilogue stores gelu' for the backward GEMM)
+__device__ __forceinline__ void gelu_erf_both2(uint64_t x2, uint64_t& y2, uint64_t& g2) {
+  const uint64_t a2 = abs2(x2);
+  const uint64_t half2 = pack2(0.5f, 0.5f);
+  const uint64_t t2 = ffma2(phi_neg_abs2(a2), pack2(-1.f, -1.f), half2);  // 0.5 - Phi(-|x|)  (>= 0)
+  y2 = ffma2(x2, half2, fmul2(a2, t2));
+  const uint64_t cdf2 = fadd2(half2, t2 | (x2 & 0x8000000080000000ull));
+  // phi(x) = 2^(-x^2 / (2 ln 2) + log2(1 / sqrt(2 pi)))
+  float e0, e1;
+  unpack2(ffma2(fmul2(x2, x2), pack2(-0.72134752044448170f, -0.72134752044448170f),
+                pack2(-1.3257480647361593f, -1.3257480647361593f)),
+          e0, e1);
+  g2 = ffma2(x2, pack2(exp2f(e0), exp2f(e1)), cdf2);
+}
 __device__ __forceinline__ uint64_t bf16x2_to_f32x2(uint32_t h) {
   return pack2(__uint_as_float(h << 16), __uint_as_float(h & 0xffff0000u));
 }
@@ -357,15 +371,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             v01 = fadd2(v01, b01);
             v23 = fadd2(v23, b23);
             if (EPI == EPI_GELU) {
-              uint2 pk;
-              pk.x = f32x2_to_bf16x2(v01);
-              pk.y = f32x2_to_bf16x2(v23);
-              if (oa) *reinterpret_cast<uint2*>(oa + (long long)it * 4 * p.ld_aux) = pk;
-              v01 = gelu_erf2(bf16x2_to_f32x2(pk.x));
-              v23 = gelu_erf2(bf16x2_to_f32x2(pk.y));
+              // the activation is evaluated on the bf16-rounded pre-activation (what HF's bf16 Linear output is);
+              // aux_out receives gelu'(x) -- all the backward GEMM needs of this layer's pre-activation
+              uint64_t g01, g23;
+              gelu_erf_both2(bf16x2_to_f32x2(f32x2_to_bf16x2(v01)), v01, g01);
+              gelu_erf_both2(bf16x2_to_f32x2(f32x2_to_bf16x2(v23)), v23, g23);
+              if (oa) {
+                uint2 pk;
+                pk.x = f32x2_to_bf16x2(g01);
+                pk.y = f32x2_to_bf16x2(g23);
+                *reinterpret_cast<uint2*>(oa + (long long)it * 4 * p.ld_aux) = pk;
+              }
             } else if (EPI == EPI_DGELU) {
-              v01 = fmul2(v01, gelu_erf_grad2(bf16x2_to_f32x2(pre_h[it].x)));
-              v23 = fmul2(v23, gelu_erf_grad2(bf16x2_to_f32x2(pre_h[it].y)));
+              v01 = fmul2(v01, bf16x2_to_f32x2(pre_h[it].x));
+              v23 = fmul2(v23, bf16x2_to_f32x2(pre_h[it].y));
             } else if (EPI == EPI_RES) {
               v01 = fadd2(v01, pack2(pre_f[it].x, pre_f[it].y));
               v23 = fadd2(v23, pack2(pre_f[it].z, pre_f[it].w));
@@ -480,17 +499,24 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
               uint2 pk;
               pk.x = pack_bf16x2(x[0], x[1]);
               pk.y = pack_bf16x2(x[2], x[3]);
-              if (p.aux_out) *reinterpret_cast<uint2*>(p.aux_out + (long long)r * p.ld_aux + col) = pk;
-              x[0] = gelu_erf(__uint_as_float(pk.x << 16));
-              x[1] = gelu_erf(__uint_as_float(pk.x & 0xffff0000u));
-              x[2] = gelu_erf(__uint_as_float(pk.y << 16));
-              x[3] = gelu_erf(__uint_as_float(pk.y & 0xffff0000u));
+              const float xb[4] = {__uint_as_float(pk.x << 16), __uint_as_float(pk.x & 0xffff0000u),
+                                   __uint_as_float(pk.y << 16), __uint_as_float(pk.y & 0xffff0000u)};
+              if (p.aux_out) {
+                uint2 gk;
+                gk.x = pack_bf16x2(gelu_erf_grad(xb[0]), gelu_erf_grad(xb[1]));
+                gk.y = pack_bf16x2(gelu_erf_grad(xb[2]), gelu_erf_grad(xb[3]));
+                *reinterpret_cast<uint2*>(p.aux_out + (long long)r * p.ld_aux + col) = gk;
+              }
+              x[0] = gelu_erf(xb[0]);
+              x[1] = gelu_erf(xb[1]);
+              x[2] = gelu_erf(xb[2]);
+              x[3] = gelu_erf(xb[3]);
             } else if (kDgelu) {
               const uint2 pk = pre_h[it];
-              x[0] *= gelu_erf_grad(__uint_as_float(pk.x << 16));
-              x[1] *= gelu_erf_grad(__uint_as_float(pk.x & 0xffff0000u));
-              x[2] *= gelu_erf_grad(__uint_as_float(pk.y << 16));
-              x[3] *= gelu_erf_grad(__uint_as_float(pk.y & 0xffff0000u));
+              x[0] *= __uint_as_float(pk.x << 16);
+              x[1] *= __uint_as_float(pk.x & 0xffff0000u);
+              x[2] *= __uint_as_float(pk.y << 16);
+              x[3] *= __uint_as_float(pk.y & 0xffff0000u);
             }
             if (kRes) {
               const float4 rv = pre_f[it];

@@ -219,21 +219,21 @@ class BlockFn(torch.autograd.Function):
         L.gemm(attn, wob, M, d, d, out_f32=x_mid, bias=bo.detach(), res=x, ldr=d)
         u2 = _empty((M, d), BF16, dev)
         L.layernorm_fwd(x_mid, ln2w.detach(), ln2b.detach(), eps, M, d, u2, stats[2], stats[3])
-        pre = _empty((M, ff), BF16, dev)
+        gp = _empty((M, ff), BF16, dev)   # gelu'(pre-activation): all the backward needs of it
         act = _empty((M, ff), BF16, dev)
-        L.gemm(u2, w1b, M, ff, d, out_bf16=act, bias=b1.detach(), act=1, aux_out=pre, ld_aux=ff)
+        L.gemm(u2, w1b, M, ff, d, out_bf16=act, bias=b1.detach(), act=1, aux_out=gp, ld_aux=ff)
         x_out = _empty((M, d), F32, dev)
         L.gemm(act, w2b, M, d, ff, out_f32=x_out, bias=b2.detach(), res=x_mid, ldr=d)
 
         ctx.st, ctx.name, ctx.geom = st, name, (M, d, ff, B, S, H, scale)
-        ctx.saved = (x, u1, stats, qkv, attn, lse, x_mid, u2, pre, act, ln1w, ln2w, wqkv, wob, w1b, w2b)
+        ctx.saved = (x, u1, stats, qkv, attn, lse, x_mid, u2, gp, act, ln1w, ln2w, wqkv, wob, w1b, w2b)
         return x_out
 
     @staticmethod
     def backward(ctx, dxo):
         st = ctx.st
         M, d, ff, B, S, H, scale = ctx.geom
-        x, u1, stats, qkv, attn, lse, x_mid, u2, pre, act, ln1w, ln2w, wqkv, wob, w1b, w2b = ctx.saved
+        x, u1, stats, qkv, attn, lse, x_mid, u2, gp, act, ln1w, ln2w, wqkv, wob, w1b, w2b = ctx.saved
         ctx.saved = None
         dev = dxo.device
         dxo = _contig_grad(dxo)
@@ -251,14 +251,15 @@ class BlockFn(torch.autograd.Function):
 
         # fc2: x_out = x_mid + act.W2^T + b2
         d_pre = _empty((M, ff), BF16, dev)
-        # GELU' fused; the epilogue also accumulates the column sums of d_pre = the fc1 bias gradient
-        L.gemm(dxob, w2b, M, ff, d, b_mn=True, ldb=ff, out_bf16=d_pre, act=2, aux_in=pre, ld_aux=ff, colsum=g_b1)
+        # x gelu' (saved by the forward epilogue) fused; the epilogue also accumulates the column sums of d_pre = the
+        # fc1 bias gradient
+        L.gemm(dxob, w2b, M, ff, d, b_mn=True, ldb=ff, out_bf16=d_pre, act=2, aux_in=gp, ld_aux=ff, colsum=g_b1)
         L.gemm(dxob, act, d, ff, M, a_mn=True, b_mn=True, lda=d, ldb=ff, out_f32=g_w2, k_splits=0)
         if cs_out is not None:
             g_b2 = cs_out
         else:
             L.colsum(dxob, M, d, g_b2)
-        del act, pre
+        del act, gp
         # fc1: pre = u2.W1^T + b1
         L.gemm(d_pre, u2, ff, d, M, a_mn=True, b_mn=True, lda=ff, ldb=d, out_f32=g_w1, k_splits=0)
         d_u2 = _empty((M, d), BF16, dev)

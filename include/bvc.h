@@ -28,7 +28,7 @@ extern "C" {
 #define BVC_ERR_ARG (-1)
 #define BVC_ERR_DRIVER (-2)
 #define BVC_ERR_LAUNCH (-3)
-#define BVC_ABI_VERSION 6
+#define BVC_ABI_VERSION 7
 
 /* library / build info: returns BVC_ABI_VERSION (bumped when a signature changes) */
 int bvc_abi_version(void);
@@ -74,8 +74,9 @@ int bvc_patchify_target(const float* pixels, const int32_t* slot, int32_t B, int
  * Requirements: lda, ldb, ldo, ld_aux multiples of 8; N multiple of 8; pointers 16-byte aligned.
  * Epilogue, in this order, per output element (r, c):
  *     v = alpha_host * (alpha_dev ? *alpha_dev : 1) * acc + (bias ? bias[c] : 0)
- *     act == 1 (GELU, exact erf, HF:316):  v = bf16(v); if aux_out: aux_out[r*ld_aux+c] = v;  v = gelu(v)
- *     act == 2 (GELU backward):            v *= gelu'(aux_in[r*ld_aux+c])
+ *     act == 1 (GELU, exact erf, HF:316):  v = bf16(v); if aux_out: aux_out[r*ld_aux+c] = bf16(gelu'(v));  v = gelu(v)
+ *     act == 2 (GELU backward):            v *= aux_in[r*ld_aux+c]      (the gelu' saved by the forward call: the
+ *                                          backward epilogue carries no transcendental math)
  *     if res:     v += res[(res_idx ? res_idx[r] : r) * ldr + c]          (fp32 residual / position table)
  *     if target:  (masked MSE, HF:672-673)  if logits_out: logits_out[r*ldo+c] = bf16(v);
  *                 v -= target[r*ldt+c];  tile partial of sum(v*v) -> loss_partial (see bvc_gemm_loss_slots)

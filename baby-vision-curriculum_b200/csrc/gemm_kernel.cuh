@@ -295,10 +295,38 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       const int tile = w / p.k_splits;
       const int m0 = (tile / p.tiles_n) * BM;
       const int n0 = (tile % p.tiles_n) * BN;
-      mbar_wait(&tmem_full[acc], acc_phase);
-      tc_fence_after();
       const int rbase = m0 + q * 32;
       const bool interior = m0 + BM <= p.M && n0 + BN <= p.N;  // warp-uniform
+      // interior fast path: the global operand of the fused epilogue (fp32 residual rows / saved gelu' factors) is
+      // software-pipelined one 32-column chunk ahead; chunk 0 is requested here, BEFORE waiting for the accumulator,
+      // so its latency hides behind this tile's MMAs instead of following them
+      float4 nxt_f[8];
+      uint2 nxt_h[8];
+      auto prefetch_chunk = [&](int cc_n) {
+        const long long r0 = rbase + rsub;
+        const int col_n = n0 + half * kColsPerWarp + cc_n + c4 * 4;
+        if (EPI == EPI_RES) {
+          const float* fb = p.res + r0 * p.ldr + col_n;
+#pragma unroll
+          for (int it = 0; it < 8; ++it)
+            asm volatile("ld.volatile.global.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(nxt_f[it].x), "=f"(nxt_f[it].y), "=f"(nxt_f[it].z), "=f"(nxt_f[it].w)
+                         : "l"(fb + (long long)it * 4 * p.ldr)
+                         : "memory");
+        }
+        if (EPI == EPI_DGELU) {
+          const bf16* hb = p.aux_in + r0 * p.ld_aux + col_n;
+#pragma unroll
+          for (int it = 0; it < 8; ++it)
+            asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];"
+                         : "=r"(nxt_h[it].x), "=r"(nxt_h[it].y)
+                         : "l"(hb + (long long)it * 4 * p.ld_aux)
+                         : "memory");
+        }
+      };
+      if (kFast && interior && (EPI == EPI_RES || EPI == EPI_DGELU)) prefetch_chunk(0);
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
       float lsum = 0.f;
 #pragma unroll 1
       for (int cc = 0; cc < kColsPerWarp; cc += 32) {
@@ -332,27 +360,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
           const uint64_t al2 = pack2(alpha, alpha);
           float4 pre_f[8];
           uint2 pre_h[8];
-          if (EPI == EPI_RES) {
-            const float* fb = p.res + r0 * p.ldr + col;
+          if (EPI == EPI_RES || EPI == EPI_DGELU) {
 #pragma unroll
-            for (int it = 0; it < 8; ++it)
-              asm volatile("ld.volatile.global.v4.f32 {%0, %1, %2, %3}, [%4];"
-                           : "=f"(pre_f[it].x), "=f"(pre_f[it].y), "=f"(pre_f[it].z), "=f"(pre_f[it].w)
-                           : "l"(fb + (long long)it * 4 * p.ldr)
-                           : "memory");
-            asm volatile("" ::"f"(pre_f[0].x), "f"(pre_f[1].x), "f"(pre_f[2].x), "f"(pre_f[3].x), "f"(pre_f[4].x),
-                         "f"(pre_f[5].x), "f"(pre_f[6].x), "f"(pre_f[7].x));
-          }
-          if (EPI == EPI_DGELU) {
-            const bf16* hb = p.aux_in + r0 * p.ld_aux + col;
-#pragma unroll
-            for (int it = 0; it < 8; ++it)
-              asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];"
-                           : "=r"(pre_h[it].x), "=r"(pre_h[it].y)
-                           : "l"(hb + (long long)it * 4 * p.ld_aux)
-                           : "memory");
-            asm volatile("" ::"r"(pre_h[0].x), "r"(pre_h[1].x), "r"(pre_h[2].x), "r"(pre_h[3].x), "r"(pre_h[4].x),
-                         "r"(pre_h[5].x), "r"(pre_h[6].x), "r"(pre_h[7].x));
+            for (int it = 0; it < 8; ++it) {
+              pre_f[it] = nxt_f[it];
+              pre_h[it] = nxt_h[it];
+            }
+            if (cc + 32 < kColsPerWarp) prefetch_chunk(cc + 32);  // in flight while this chunk is processed
           }
           // the dispatcher (gemm.cu) guarantees: EPI_RES writes fp32 only, the other fast variants bf16 only
           bf16* ob = EPI != EPI_RES ? p.out_bf16 + r0 * p.ldo + col : nullptr;

@@ -11,6 +11,8 @@ operands bf16, accumulation fp32, LayerNorm / softmax statistics fp32, master we
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import _lib as L
@@ -160,6 +162,46 @@ def _contig_grad(g):
     return g if g.is_contiguous() else g.contiguous()
 
 
+# Weight-gradient GEMMs of a block do not feed the rest of its backward.  Launched on a second stream, each one starts
+# on the SMs that the main stream's current GEMM leaves idle in its last, partial wave of tiles (the kernels are
+# persistent with one CTA per SM, and e.g. the 240 tiles of an M = 10240, N = 768 GEMM fill 148 SMs to 81 %), instead of
+# queueing behind it.  BVC_WGRAD_STREAM=0 keeps everything on one stream.
+_WGRAD_STREAM = os.environ.get("BVC_WGRAD_STREAM", "1") != "0"
+_wgrad_streams = {}
+
+
+class _SideStream:
+    """`with side.after_main(): launch(...)` enqueues on the side stream behind everything queued so far on the
+    current stream; join() makes the current stream wait for the side stream."""
+
+    def __init__(self, dev):
+        self.stream = _wgrad_streams.get(dev)
+        if self.stream is None:
+            self.stream = _wgrad_streams[dev] = torch.cuda.Stream(device=dev)
+        self.used = False
+
+    def after_main(self):
+        ev = torch.cuda.Event()
+        ev.record()
+        self.stream.wait_event(ev)
+        self.used = True
+        return torch.cuda.stream(self.stream)
+
+    def join(self):
+        if self.used:
+            torch.cuda.current_stream().wait_stream(self.stream)
+            self.used = False
+
+
+class _NoSideStream:
+    def after_main(self):
+        import contextlib
+        return contextlib.nullcontext()
+
+    def join(self):
+        pass
+
+
 # ==================================================================================================== embed
 class EmbedFn(torch.autograd.Function):
     """e = W_pe . patch + b_pe + pos[vis_idx]  on the visible tubelets only (HF:164-177, HF:109-122)."""
@@ -238,6 +280,7 @@ class BlockFn(torch.autograd.Function):
         dev = dxo.device
         dxo = _contig_grad(dxo)
         dxob, cs_out = st.side.take(dxo, M, d)
+        wg = _SideStream(dev) if _WGRAD_STREAM else _NoSideStream()  # operands stay referenced until wg.join() below
 
         # every atomically-accumulated output of this block in one zero-filled buffer (one memset); the last slot
         # collects colsum(dx) of this block's input gradient for the stage upstream
@@ -254,17 +297,17 @@ class BlockFn(torch.autograd.Function):
         # x gelu' (saved by the forward epilogue) fused; the epilogue also accumulates the column sums of d_pre = the
         # fc1 bias gradient
         L.gemm(dxob, w2b, M, ff, d, b_mn=True, ldb=ff, out_bf16=d_pre, act=2, aux_in=gp, ld_aux=ff, colsum=g_b1)
-        L.gemm(dxob, act, d, ff, M, a_mn=True, b_mn=True, lda=d, ldb=ff, out_f32=g_w2, k_splits=0)
+        with wg.after_main():
+            L.gemm(dxob, act, d, ff, M, a_mn=True, b_mn=True, lda=d, ldb=ff, out_f32=g_w2, k_splits=0)
         if cs_out is not None:
             g_b2 = cs_out
         else:
             L.colsum(dxob, M, d, g_b2)
-        del act, gp
         # fc1: pre = u2.W1^T + b1
-        L.gemm(d_pre, u2, ff, d, M, a_mn=True, b_mn=True, lda=ff, ldb=d, out_f32=g_w1, k_splits=0)
         d_u2 = _empty((M, d), BF16, dev)
         L.gemm(d_pre, w1b, M, d, ff, b_mn=True, ldb=d, out_bf16=d_u2)
-        del d_pre, u2
+        with wg.after_main():
+            L.gemm(d_pre, u2, ff, d, M, a_mn=True, b_mn=True, lda=ff, ldb=d, out_f32=g_w1, k_splits=0)
         # LN2 backward + residual branch
         dxm = _empty((M, d), F32, dev)
         dxmb = _empty((M, d), BF16, dev)
@@ -274,23 +317,24 @@ class BlockFn(torch.autograd.Function):
         # attention output projection: x_mid = x + attn.Wo^T + bo
         d_attn = _empty((M, d), BF16, dev)
         L.gemm(dxmb, wob, M, d, d, b_mn=True, ldb=d, out_bf16=d_attn)
-        L.gemm(dxmb, attn, d, d, M, a_mn=True, b_mn=True, lda=d, ldb=d, out_f32=g_wo, k_splits=0)
+        with wg.after_main():
+            L.gemm(dxmb, attn, d, d, M, a_mn=True, b_mn=True, lda=d, ldb=d, out_f32=g_wo, k_splits=0)
         # attention core
         dqkv = _empty((M, 3 * d), BF16, dev)
         delta = _empty((B, H, S), F32, dev)
         L.attn_bwd(qkv, attn, d_attn, lse, B, S, H, scale, delta, dqkv)
-        del d_attn, attn, qkv
         # fused QKV projection
-        L.gemm(dqkv, u1, 3 * d, d, M, a_mn=True, b_mn=True, lda=3 * d, ldb=d, out_f32=g_wqkv, k_splits=0)
-        L.colsum(dqkv, M, 3 * d, g_bqkv)
         d_u1 = _empty((M, d), BF16, dev)
         L.gemm(dqkv, wqkv, M, d, 3 * d, b_mn=True, ldb=d, out_bf16=d_u1)
-        del dqkv, u1
+        with wg.after_main():
+            L.gemm(dqkv, u1, 3 * d, d, M, a_mn=True, b_mn=True, lda=3 * d, ldb=d, out_f32=g_wqkv, k_splits=0)
+            L.colsum(dqkv, M, 3 * d, g_bqkv)
         # LN1 backward + residual
         dx = _empty((M, d), F32, dev)
         dxb = _empty((M, d), BF16, dev)
         L.layernorm_bwd(d_u1, x, stats[0], stats[1], ln1w.detach(), dxm, M, d, dx, dxb, g_ln1w, g_ln1b, dxsum=cs_in)
         st.side.put(dx, dxb, cs_in)
+        wg.join()  # the weight gradients are complete on the current stream from here on
         st.reduce(flat)
 
         gw = g_wqkv.view(3, d, d)

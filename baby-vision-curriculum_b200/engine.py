@@ -170,6 +170,14 @@ _WGRAD_STREAM = os.environ.get("BVC_WGRAD_STREAM", "1") != "0"
 _wgrad_streams = {}
 
 
+def set_wgrad_stream(on: bool) -> bool:
+    """Enable / disable the second stream (returns the previous setting).  bench.py turns it off for its per-kernel
+    timing pass: concurrent kernels share the SMs, so their individual event durations stop being kernel times."""
+    global _WGRAD_STREAM
+    old, _WGRAD_STREAM = _WGRAD_STREAM, bool(on)
+    return old
+
+
 class _SideStream:
     """`with side.after_main(): launch(...)` enqueues on the side stream behind everything queued so far on the
     current stream; join() makes the current stream wait for the side stream."""

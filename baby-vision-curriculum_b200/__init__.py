@@ -15,3 +15,4 @@ from .masking import TubeMaskingGenerator, RandomMaskingGenerator, batch_masks  
 from .ddputils import AllReduce  # noqa: F401
 from .optim import FusedSGD  # noqa: F401
 from .ddp import DistributedDataParallel  # noqa: F401
+from .simclr import info_nce_loss, get_special_matrix, make_masks as make_simclr_masks  # noqa: F401

@@ -12,7 +12,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libbvc.so")
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 _lib = None
 
@@ -63,6 +63,15 @@ _SIGNATURES = {
                                C.c_void_p]),
     "bvc_attn_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                                C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "bvc_nce_normalize_split": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_float, C.c_void_p,
+                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "bvc_nce_partial_slots": (C.c_int64, [C.c_int32]),
+    "bvc_nce_loss": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
+                               C.c_void_p]),
+    "bvc_nce_grad": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
+                               C.c_void_p, C.c_void_p]),
+    "bvc_nce_normalize_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_int32, C.c_int32,
+                                        C.c_float, C.c_void_p, C.c_void_p]),
     "bvc_sgd_step": (C.c_int, [C.c_void_p, C.c_int32, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int32,
                                C.c_void_p, C.c_void_p, C.c_void_p]),
 }
@@ -310,4 +319,42 @@ def sgd_step(table, n_entries, total_elems, lr, momentum, dampening, weight_deca
     with _Timed("sgd_step", 0.0, float(total_elems) * bytes_per_elem):
         _check(load().bvc_sgd_step(_p(table), n_entries, lr, momentum, dampening, weight_decay, 1 if nesterov else 0,
                                    _p(grad_scale), _p(found_inf), _stream()), "bvc_sgd_step")
+    _count()
+
+
+def nce_normalize_split(feats, n, D, eps, a_split, b_split, bk_split, inv_norm):
+    _cuda(feats, a_split, b_split, bk_split, inv_norm)
+    is_bf16 = 1 if feats.dtype == torch.bfloat16 else 0
+    with _Timed("nce_rows", 0.0, float(n) * D * (feats.element_size() + 18)):
+        _check(load().bvc_nce_normalize_split(_p(feats), is_bf16, feats.stride(0), n, D, eps, _p(a_split), _p(b_split),
+                                              _p(bk_split), _p(inv_norm), _stream()), "bvc_nce_normalize_split")
+    _count()
+
+
+def nce_partial_slots(n):
+    return int(load().bvc_nce_partial_slots(n))
+
+
+def nce_loss(S, pos_u8, neg_u8, n, partials, out4):
+    _cuda(S, pos_u8, neg_u8, partials, out4)
+    with _Timed("nce_loss", 0.0, float(n) * n * 6):
+        _check(load().bvc_nce_loss(_p(S), S.stride(0), _p(pos_u8), _p(neg_u8), n, _p(partials), _p(out4), _stream()),
+               "bvc_nce_loss")
+    _count(2)
+
+
+def nce_grad(S, pos_u8, neg_u8, n, out4, grad_out, g_split):
+    _cuda(S, pos_u8, neg_u8, out4, grad_out, g_split)
+    with _Timed("nce_grad", 0.0, float(n) * n * 14):
+        _check(load().bvc_nce_grad(_p(S), S.stride(0), _p(pos_u8), _p(neg_u8), n, _p(out4), _p(grad_out), _p(g_split),
+                                   _stream()), "bvc_nce_grad")
+    _count()
+
+
+def nce_normalize_bwd(dfhat, feats, inv_norm, n, D, eps, dfeats):
+    _cuda(dfhat, feats, inv_norm, dfeats)
+    is_bf16 = 1 if feats.dtype == torch.bfloat16 else 0
+    with _Timed("nce_rows", 0.0, float(n) * D * (feats.element_size() + 8)):
+        _check(load().bvc_nce_normalize_bwd(_p(dfhat), _p(feats), is_bf16, feats.stride(0), _p(inv_norm), n, D, eps,
+                                            _p(dfeats), _stream()), "bvc_nce_normalize_bwd")
     _count()

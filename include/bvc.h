@@ -28,7 +28,7 @@ extern "C" {
 #define BVC_ERR_ARG (-1)
 #define BVC_ERR_DRIVER (-2)
 #define BVC_ERR_LAUNCH (-3)
-#define BVC_ABI_VERSION 7
+#define BVC_ABI_VERSION 8
 
 /* library / build info: returns BVC_ABI_VERSION (bumped when a signature changes) */
 int bvc_abi_version(void);
@@ -193,6 +193,31 @@ int bvc_attn_bwd(const void* qkv, const void* out, const void* dout, const float
 int bvc_sgd_step(const void* table, int32_t n_entries, float lr, float momentum, float dampening,
                  float weight_decay, int32_t nesterov, const float* grad_scale, const float* found_inf,
                  void* stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * SimCLR loss of the contrastive path (pretraining/contrastive/pretrain_simclr.py:114-128 info_nce_loss with the
+ * masks of :86-91 / :284-292).  With S = cos_sim(feats_i, feats_j) / T:
+ *     loss = logsumexp(S[neg_mask]) - mean(S[pos_mask])          (ONE global log-sum-exp, as the reference computes)
+ * The similarity runs on bvc_gemm_bf16; these entry points are the passes around it (the host side strings them
+ * together: baby-vision-curriculum_b200/simclr.py).  n % 8 == 0, D % 8 == 0.
+ *   bvc_nce_normalize_split : f^ = feats / max(|feats|, eps) per row, split into bf16 hi + lo;
+ *        a_split [n,3D] = [hi|lo|hi], b_split [n,3D] = [hi|hi|lo]  ->  S = (1/T) * a_split . b_split^T (K = 3D)
+ *        bk_split [3n,D] = [hi;hi;lo]  (B operand, MN-major, of the backward GEMM);  inv_norm fp32 [n]
+ *   bvc_nce_loss  : masked pass over S fp32 [n,n] -> out4 = {loss, lse, mean_pos, pos_count};
+ *        partials = scratch of bvc_nce_partial_slots(n) floats.  Masks are uint8 / bool [n,n], arbitrary.
+ *   bvc_nce_grad  : g_split [n,3n] = [hi|lo|hi] of  grad_out * ((neg_ij + neg_ji) exp(S_ij - lse) - (pos_ij + pos_ji)/P)
+ *        ->  dF^ [n,D] = (1/T) * g_split . bk_split   (bvc_gemm_bf16, b_mn_major = 1, K = 3n)
+ *   bvc_nce_normalize_bwd : dfeats = (dF^ - f^ (f^ . dF^)) * inv_norm
+ * ------------------------------------------------------------------------------------------------------ */
+int bvc_nce_normalize_split(const void* feats, int32_t feats_is_bf16, int64_t ld, int32_t n, int32_t D, float eps,
+                            void* a_split, void* b_split, void* bk_split, float* inv_norm, void* stream);
+int64_t bvc_nce_partial_slots(int32_t n);
+int bvc_nce_loss(const float* S, int64_t lds, const uint8_t* pos_mask, const uint8_t* neg_mask, int32_t n,
+                 float* partials, float* out4, void* stream);
+int bvc_nce_grad(const float* S, int64_t lds, const uint8_t* pos_mask, const uint8_t* neg_mask, int32_t n,
+                 const float* out4, const float* grad_out, void* g_split, void* stream);
+int bvc_nce_normalize_bwd(const float* dfhat, const void* feats, int32_t feats_is_bf16, int64_t ld,
+                          const float* inv_norm, int32_t n, int32_t D, float eps, float* dfeats, void* stream);
 
 #ifdef __cplusplus
 }

@@ -51,3 +51,15 @@ def grad_report(grads, ref):
         num += e * e
         den += n * n
     return rows, (num / max(den, 1e-60)) ** 0.5
+
+
+def simclr_feats(g):
+    """Features of a tests/golden/simclr_*.npz fixture: stored for the small cases, regenerated from the numpy seed
+    (checked against the stored checksum) for the large one -- tools/make_golden_simclr.py."""
+    if "feats" in g.files:
+        return torch.from_numpy(g["feats"])
+    n, D, scale = int(g["n"]), int(g["D"]), float(g["scale"])
+    feats = torch.from_numpy(np.random.default_rng(100 + n).standard_normal((n, D)).astype(np.float32)) * scale
+    feats[1::2] = 0.7 * feats[0::2] + 0.3 * feats[1::2]
+    assert abs(float(feats.double().sum()) - float(g["feats_checksum"])) < 1e-6
+    return feats

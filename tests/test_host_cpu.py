@@ -122,3 +122,22 @@ def test_fused_sgd_host_side():
     p.grad = torch.ones(8)
     with pytest.raises(bvc.BvcError):
         opt.step()
+
+
+def test_simclr_host_side(golden_dir):
+    """get_special_matrix / make_masks mirror pretrain_simclr.py:86-91, 285-291 bit-exactly (fixture from the reference's
+    own function); info_nce_loss refuses CPU tensors (no CPU fallback) and bad shapes."""
+    import os
+    import numpy as np
+    import pytest
+    import torch
+    import bvc_b200 as bvc
+    g = np.load(os.path.join(golden_dir, "simclr_tiny.npz"))
+    assert np.array_equal(bvc.get_special_matrix(16), g["special"])
+    pos, neg = bvc.make_simclr_masks(16, "cpu")
+    assert pos.dtype == torch.bool and int(pos.sum()) == 30 and int(neg.sum()) == 16 * 16 - 16 - 30
+    assert not bool((pos & neg).any()) and not bool(neg.diagonal().any())
+    with pytest.raises(bvc.BvcError):
+        bvc.info_nce_loss(0.1, (pos, neg), torch.zeros(16, 32))
+    with pytest.raises(ValueError):
+        bvc.info_nce_loss(0.1, (pos, neg), torch.zeros(16))

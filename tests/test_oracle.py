@@ -112,3 +112,26 @@ def test_small_step_summary(golden_dir):
 
 def test_loss_allreduce_is_mean():
     assert abs(O.loss_allreduce([1.0, 3.0]) - 2.0) < 1e-12
+
+
+# ------------------------------------------------------------------------------------------------ SimCLR loss oracle
+@pytest.mark.parametrize("tag", ["tiny", "ref", "cfg3"])
+def test_simclr_oracle_vs_reference_golden(golden_dir, tag):
+    """oracle/simclr_oracle.py against fixtures produced by the reference's own info_nce_loss / get_special_matrix
+    (tools/make_golden_simclr.py): masks bit-equal, loss and gradients to fp64 round-off."""
+    import numpy as np
+    import torch
+    from oracle import simclr_oracle as SO
+    g = np.load(os.path.join(golden_dir, f"simclr_{tag}.npz"))
+    from tests.helpers import simclr_feats
+    feats = simclr_feats(g)
+    n = feats.shape[0]
+    assert np.array_equal(SO.get_special_matrix(min(n, 16)), g["special"])
+    loss, grad = SO.loss_and_grad(float(g["temperature"]), SO.make_masks(n), feats)
+    assert abs(float(loss) - float(g["loss_f64"])) <= 1e-10 * abs(float(g["loss_f64"]))
+    assert abs(float(grad.norm()) - float(g["grad_norm_f64"])) <= 1e-9 * float(g["grad_norm_f64"])
+    ref = torch.from_numpy(g["grad_f64"])
+    got = grad if n <= 64 else grad[:8]
+    assert float((got - ref).norm() / ref.norm()) <= 1e-9
+    # the reference's own fp32 run differs from fp64 by this much (context for the GPU tolerance)
+    assert abs(float(g["loss_f32"]) - float(g["loss_f64"])) <= 1e-5 * abs(float(g["loss_f64"]))

@@ -12,7 +12,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libbvc.so")
-ABI_VERSION = 8
+ABI_VERSION = 9
 
 _lib = None
 
@@ -43,6 +43,8 @@ _SIGNATURES = {
                                     C.c_void_p, C.c_void_p]),
     "bvc_patchify_target": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int32] * 8 + [C.c_void_p, C.c_void_p, C.c_int32,
                                                                                   C.c_void_p]),
+    "bvc_patchify_target_u8": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_void_p] +
+                               [C.c_int32] * 8 + [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "bvc_gemm_bf16": (C.c_int, [C.POINTER(GemmArgs), C.c_void_p]),
     "bvc_gemm_loss_slots": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32]),
     "bvc_loss_finalize": (C.c_int, [C.c_void_p, C.c_int64, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -177,12 +179,23 @@ def mask_to_index(mask_u8, nv, vis_idx, msk_idx, slot, status):
     _count()
 
 
-def patchify_target(pixels, slot, ts, ps, nv, patches_vis, target, norm_pix=True):
+def patchify_target(pixels, slot, ts, ps, nv, patches_vis, target, norm_pix=True, pixel_norm=None):
+    """pixels fp32 [B,T,C,H,W], or uint8 with pixel_norm = (mean[3], std[3]) (the dataset's Normalize, applied in-kernel)."""
     _cuda(pixels, slot, patches_vis, target)
     B, T, Cc, H, W = pixels.shape
-    with _Timed("patchify_target", 0.0, float(pixels.numel() * 4 + patches_vis.numel() * 2 + target.numel() * 4)):
-        _check(load().bvc_patchify_target(_p(pixels), _p(slot), B, T, Cc, H, W, ts, ps, nv, _p(patches_vis), _p(target),
-                                          1 if norm_pix else 0, _stream()), "bvc_patchify_target")
+    nbytes = float(pixels.numel() * pixels.element_size() + patches_vis.numel() * 2 + target.numel() * 4)
+    with _Timed("patchify_target", 0.0, nbytes):
+        if pixels.dtype == torch.uint8:
+            if pixel_norm is None:
+                raise BvcError("uint8 pixels need pixel_norm=(mean, std)")
+            mean = (C.c_float * 3)(*[float(v) for v in pixel_norm[0]])
+            std = (C.c_float * 3)(*[float(v) for v in pixel_norm[1]])
+            _check(load().bvc_patchify_target_u8(_p(pixels), mean, std, _p(slot), B, T, Cc, H, W, ts, ps, nv,
+                                                 _p(patches_vis), _p(target), 1 if norm_pix else 0, _stream()),
+                   "bvc_patchify_target_u8")
+        else:
+            _check(load().bvc_patchify_target(_p(pixels), _p(slot), B, T, Cc, H, W, ts, ps, nv, _p(patches_vis),
+                                              _p(target), 1 if norm_pix else 0, _stream()), "bvc_patchify_target")
     _count()
 
 

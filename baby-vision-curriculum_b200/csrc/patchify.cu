@@ -70,17 +70,25 @@ __device__ __constant__ float kInMean[3] = {0.485f, 0.456f, 0.406f};
 constexpr int kPatchConsumers = 7;
 constexpr int kPatchThreads = 32 * (1 + kPatchConsumers);
 
-template <int TS>
+// U8: the clip arrives as uint8 frames (4x fewer bytes over PCIe and from HBM) and the dataset's ToTensor + Normalize
+// (homeview.py:218-231: x / 255, then (x - mean) / std per channel) is applied here, in registers, with IEEE
+// divisions in torchvision's operation order -- bit-identical to normalising on the host.
+struct PixelNorm {
+  float mean[3], std[3];
+};
+
+template <int TS, bool U8>
 __global__ void __launch_bounds__(kPatchThreads, 1) patchify_target_kernel(const __grid_constant__ CUtensorMap tmap,
                                                                            const int* __restrict__ slot, int Tg, int Hg,
                                                                            int Wg, int split, int n_items, int n_stages,
                                                                            int nv, int N, bf16* __restrict__ patches_vis,
-                                                                           float* __restrict__ target, int norm_pix) {
+                                                                           float* __restrict__ target, int norm_pix,
+                                                                           PixelNorm pn) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
   const int TB = Wg / split;   // tubelets per box
   const int BW = TB * 16;      // pixels per box row
-  const int box_bytes = TS * 3 * 16 * BW * 4;
+  const int box_bytes = TS * 3 * 16 * BW * (U8 ? 1 : 4);
   uint64_t* full = reinterpret_cast<uint64_t*>(base + (size_t)n_stages * box_bytes);
   uint64_t* empty = full + n_stages;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -115,7 +123,8 @@ __global__ void __launch_bounds__(kPatchThreads, 1) patchify_target_kernel(const
     for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
       const int sp = w % split, hg = (w / split) % Hg, tg = (w / (split * Hg)) % Tg, b = w / (split * Hg * Tg);
       const int st = it % n_stages;
-      const float* tile = reinterpret_cast<const float*>(base + (size_t)st * box_bytes);
+      const uint8_t* tile_b = base + (size_t)st * box_bytes;
+      const float* tile = reinterpret_cast<const float*>(tile_b);
       mbar_wait(&full[st], (uint32_t)(it / n_stages) & 1u);
       for (int wl = cw; wl < TB; wl += kPatchConsumers) {
         const int n = (tg * Hg + hg) * Wg + sp * TB + wl;
@@ -125,7 +134,17 @@ __global__ void __launch_bounds__(kPatchThreads, 1) patchify_target_kernel(const
 #pragma unroll
         for (int i = 0; i < NI; ++i) {
           const int row = i * 8 + sub_row;  // = (t*3 + c)*16 + ph
-          v[i] = *reinterpret_cast<const float4*>(tile + (long long)row * BW + wl * 16 + chunk * 4);
+          if (U8) {
+            const uchar4 u = *reinterpret_cast<const uchar4*>(tile_b + (long long)row * BW + wl * 16 + chunk * 4);
+            const int c = (i >> 1) % 3;
+            const float mu = pn.mean[c], sd = pn.std[c];
+            v[i].x = __fdiv_rn(__fsub_rn(__fdiv_rn((float)u.x, 255.f), mu), sd);
+            v[i].y = __fdiv_rn(__fsub_rn(__fdiv_rn((float)u.y, 255.f), mu), sd);
+            v[i].z = __fdiv_rn(__fsub_rn(__fdiv_rn((float)u.z, 255.f), mu), sd);
+            v[i].w = __fdiv_rn(__fsub_rn(__fdiv_rn((float)u.w, 255.f), mu), sd);
+          } else {
+            v[i] = *reinterpret_cast<const float4*>(tile + (long long)row * BW + wl * 16 + chunk * 4);
+          }
         }
         if (s < nv) {
           // visible: bf16 row in Conv3d K-order k = ((c*TS + t)*16 + ph)*16 + pw
@@ -210,31 +229,34 @@ extern "C" int bvc_mask_to_index(const uint8_t* mask, int32_t B, int32_t N, int3
   return BVC_OK;
 }
 
-extern "C" int bvc_patchify_target(const float* pixels, const int32_t* slot, int32_t B, int32_t T, int32_t C, int32_t H,
-                                   int32_t W, int32_t ts, int32_t ps, int32_t nv, void* patches_vis, float* target,
-                                   int32_t norm_pix, void* stream) {
+static int patchify_launch(const void* pixels, bool u8, PixelNorm pn, const int32_t* slot, int32_t B, int32_t T,
+                           int32_t C, int32_t H, int32_t W, int32_t ts, int32_t ps, int32_t nv, void* patches_vis,
+                           float* target, int32_t norm_pix, void* stream) {
   BVC_CHECK_ARG(pixels && slot && patches_vis && target);
   BVC_CHECK_ARG(C == 3 && ps == 16 && (ts == 1 || ts == 2));
   BVC_CHECK_ARG(B > 0 && T % ts == 0 && H % 16 == 0 && W % 16 == 0 && W <= 256);
   BVC_CHECK_ARG((((uintptr_t)pixels) & 15) == 0);
+  const int esz = u8 ? 1 : 4;
   const int Tg = T / ts, Hg = H / 16, Wg = W / 16;
   const int N = Tg * Hg * Wg;
   BVC_CHECK_ARG(nv >= 0 && nv <= N);
   // column split: the widest box (whole tubelets) that keeps a stage <= 48 KB, so several stages fit per SM
   int split = 1;
-  while (split < Wg && ((size_t)ts * 3 * 16 * (W / split) * 4 > 48 * 1024 || Wg % split != 0)) ++split;
+  while (split < Wg && ((size_t)ts * 3 * 16 * (W / split) * esz > 48 * 1024 || Wg % split != 0)) ++split;
   BVC_CHECK_ARG(Wg % split == 0);
   const int BW = W / split;
-  const size_t box_bytes = (size_t)ts * 3 * 16 * BW * 4;
+  const size_t box_bytes = (size_t)ts * 3 * 16 * BW * esz;
+  BVC_CHECK_ARG(box_bytes % 128 == 0);  // every stage of the ring starts 128-byte aligned
   int n_stages = (int)((200 * 1024) / box_bytes);
   if (n_stages > 6) n_stages = 6;
   BVC_CHECK_ARG(n_stages >= 2);
   CUtensorMap tm;
   const uint64_t dims[5] = {(uint64_t)W, (uint64_t)H, 3, (uint64_t)T, (uint64_t)B};
-  const uint64_t strides[4] = {(uint64_t)W * 4, (uint64_t)W * H * 4, (uint64_t)W * H * 3 * 4,
-                               (uint64_t)W * H * 3 * T * 4};
+  const uint64_t strides[4] = {(uint64_t)W * esz, (uint64_t)W * H * esz, (uint64_t)W * H * 3 * esz,
+                               (uint64_t)W * H * 3 * T * esz};
   const uint32_t box[5] = {(uint32_t)BW, 16, 3, (uint32_t)ts, 1};
-  int rc = make_tmap(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, pixels, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE);
+  int rc = make_tmap(&tm, u8 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, pixels, dims, strides,
+                     box, CU_TENSOR_MAP_SWIZZLE_NONE);
   if (rc) return rc;
   const size_t smem = (size_t)n_stages * box_bytes + 2 * n_stages * sizeof(uint64_t) + 128;
   cudaStream_t st = (cudaStream_t)stream;
@@ -242,26 +264,45 @@ extern "C" int bvc_patchify_target(const float* pixels, const int32_t* slot, int
   BVC_CHECK_ARG(n_items_ll < (1ll << 31));
   const int n_items = (int)n_items_ll;
   const int grid = n_items < num_sms() ? n_items : num_sms();  // persistent: one CTA per SM
-  static bool attr1 = false, attr2 = false;
-  if (ts == 1) {
-    if (!attr1) {
-      if (cudaFuncSetAttribute(patchify_target_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024) !=
-          cudaSuccess)
-        return BVC_ERR_LAUNCH;
-      attr1 = true;
-    }
-    patchify_target_kernel<1><<<grid, kPatchThreads, smem, st>>>(tm, slot, Tg, Hg, Wg, split, n_items, n_stages, nv, N,
-                                                                 (bf16*)patches_vis, target, norm_pix);
-  } else {
-    if (!attr2) {
-      if (cudaFuncSetAttribute(patchify_target_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024) !=
-          cudaSuccess)
-        return BVC_ERR_LAUNCH;
-      attr2 = true;
-    }
-    patchify_target_kernel<2><<<grid, kPatchThreads, smem, st>>>(tm, slot, Tg, Hg, Wg, split, n_items, n_stages, nv, N,
-                                                                 (bf16*)patches_vis, target, norm_pix);
+  static bool attr_done = false;
+  if (!attr_done) {
+    if (cudaFuncSetAttribute(patchify_target_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024) !=
+            cudaSuccess ||
+        cudaFuncSetAttribute(patchify_target_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024) !=
+            cudaSuccess ||
+        cudaFuncSetAttribute(patchify_target_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024) !=
+            cudaSuccess ||
+        cudaFuncSetAttribute(patchify_target_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024) !=
+            cudaSuccess)
+      return BVC_ERR_LAUNCH;
+    attr_done = true;
   }
+#define BVC_PATCHIFY_LAUNCH(TS_, U8_)                                                                                  \
+  patchify_target_kernel<TS_, U8_><<<grid, kPatchThreads, smem, st>>>(tm, slot, Tg, Hg, Wg, split, n_items, n_stages, \
+                                                                      nv, N, (bf16*)patches_vis, target, norm_pix, pn)
+  if (ts == 1) {
+    if (u8) BVC_PATCHIFY_LAUNCH(1, true);
+    else BVC_PATCHIFY_LAUNCH(1, false);
+  } else {
+    if (u8) BVC_PATCHIFY_LAUNCH(2, true);
+    else BVC_PATCHIFY_LAUNCH(2, false);
+  }
+#undef BVC_PATCHIFY_LAUNCH
   BVC_CHECK_LAUNCH();
   return BVC_OK;
+}
+
+extern "C" int bvc_patchify_target(const float* pixels, const int32_t* slot, int32_t B, int32_t T, int32_t C, int32_t H,
+                                   int32_t W, int32_t ts, int32_t ps, int32_t nv, void* patches_vis, float* target,
+                                   int32_t norm_pix, void* stream) {
+  PixelNorm pn{{0.f, 0.f, 0.f}, {1.f, 1.f, 1.f}};
+  return patchify_launch(pixels, false, pn, slot, B, T, C, H, W, ts, ps, nv, patches_vis, target, norm_pix, stream);
+}
+
+extern "C" int bvc_patchify_target_u8(const uint8_t* pixels, const float* mean3, const float* std3, const int32_t* slot,
+                                      int32_t B, int32_t T, int32_t C, int32_t H, int32_t W, int32_t ts, int32_t ps,
+                                      int32_t nv, void* patches_vis, float* target, int32_t norm_pix, void* stream) {
+  BVC_CHECK_ARG(mean3 && std3 && std3[0] != 0.f && std3[1] != 0.f && std3[2] != 0.f);
+  PixelNorm pn{{mean3[0], mean3[1], mean3[2]}, {std3[0], std3[1], std3[2]}};
+  return patchify_launch(pixels, true, pn, slot, B, T, C, H, W, ts, ps, nv, patches_vis, target, norm_pix, stream);
 }

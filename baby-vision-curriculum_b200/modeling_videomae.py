@@ -194,6 +194,7 @@ class VideoMAEForPreTraining(nn.Module):
         self._pos_dev = {}
         self._cache = Bf16Cache()
         self._grad_sync = None   # set by bvc_b200.DistributedDataParallel (ddp.py)
+        self._pixel_norm = None  # (mean[3], std[3]) for uint8 pixel_values, see set_input_normalization
         self._nv = None          # cached visible-token count (validated on device every step)
         self._status = None      # device int32 flag: a mask row violated the equal-count contract
         self._strict = os.environ.get("BVC_STRICT_MASK", "0") == "1"
@@ -235,6 +236,17 @@ class VideoMAEForPreTraining(nn.Module):
         ents.append(("head", "w", (self.decoder.head.weight,)))
         return ents
 
+    def set_input_normalization(self, mean, std):
+        """Accept uint8 clips: `model(pixel_values_uint8, ...)` then applies the dataset's ToTensor + Normalize
+        (pretraining/generative/homeview.py:218-231, `Normalize(mean, std)` after `/ 255`) inside the patchify kernel --
+        bit-identical to normalising on the host, at a quarter of the host->device and HBM bytes.
+        The reference's transform is mean = std-per-channel constants (0.5, 0.25)."""
+        mean, std = tuple(float(v) for v in mean), tuple(float(v) for v in std)
+        if len(mean) != 3 or len(std) != 3 or any(v == 0.0 for v in std):
+            raise ValueError("mean / std must have 3 entries, std non-zero")
+        self._pixel_norm = (mean, std)
+        return self
+
     def weight_shadows(self):
         """bf16 / packed-bias operand copies of the weights, for an optimizer that refreshes them in its own pass."""
         return self._cache.shadows()
@@ -270,7 +282,11 @@ class VideoMAEForPreTraining(nn.Module):
         if tuple(bool_masked_pos.shape) != (B, N):
             raise ValueError(f"bool_masked_pos must be [{B}, {N}]")
         x = pixel_values.detach()
-        if x.dtype != F32 or not x.is_contiguous():
+        if x.dtype == torch.uint8:
+            if self._pixel_norm is None:
+                raise ValueError("uint8 pixel_values need model.set_input_normalization(mean, std) first")
+            x = x.contiguous()
+        elif x.dtype != F32 or not x.is_contiguous():
             x = x.to(F32).contiguous()
         m = bool_masked_pos.to(device=dev)
         m = (m if m.dtype == torch.bool else m != 0).contiguous().view(torch.uint8)
@@ -304,7 +320,8 @@ class VideoMAEForPreTraining(nn.Module):
             patches = torch.empty((B * nv, K), dtype=BF16, device=dev)
             target = torch.empty((B * nm, K), dtype=F32, device=dev)
             L.patchify_target(x, st.slot, c.tubelet_size, c.patch_size, nv, patches, target,
-                              bool(getattr(c, "norm_pix_loss", True)))
+                              bool(getattr(c, "norm_pix_loss", True)),
+                              pixel_norm=self._pixel_norm if x.dtype == torch.uint8 else None)
 
             pos_e, pos_d = self._pos(dev)
             proj = self.videomae.embeddings.patch_embeddings.projection

@@ -28,7 +28,7 @@ extern "C" {
 #define BVC_ERR_ARG (-1)
 #define BVC_ERR_DRIVER (-2)
 #define BVC_ERR_LAUNCH (-3)
-#define BVC_ABI_VERSION 8
+#define BVC_ABI_VERSION 9
 
 /* library / build info: returns BVC_ABI_VERSION (bumped when a signature changes) */
 int bvc_abi_version(void);
@@ -61,6 +61,13 @@ int bvc_mask_to_index(const uint8_t* mask, int32_t B, int32_t N, int32_t nv, int
 int bvc_patchify_target(const float* pixels, const int32_t* slot, int32_t B, int32_t T, int32_t C, int32_t H,
                         int32_t W, int32_t ts, int32_t ps, int32_t nv, void* patches_vis, float* target,
                         int32_t norm_pix, void* stream);
+/* Same pass on uint8 frames [B,T,C,H,W]: the dataset's ToTensor + Normalize
+ * (pretraining/generative/homeview.py:218-231: x / 255, then (x - mean[c]) / std[c]) is applied in registers with IEEE
+ * divisions in torchvision's operation order, so the outputs are bit-identical to normalising on the host and calling
+ * bvc_patchify_target; the clip crosses PCIe and HBM at a quarter of the bytes.  mean3 / std3 are HOST pointers. */
+int bvc_patchify_target_u8(const uint8_t* pixels, const float* mean3, const float* std3, const int32_t* slot, int32_t B,
+                           int32_t T, int32_t C, int32_t H, int32_t W, int32_t ts, int32_t ps, int32_t nv,
+                           void* patches_vis, float* target, int32_t norm_pix, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------
  * Dense contraction on the tcgen05 tensor cores:   out[M,N] = epilogue( alpha * A[M,K] . B[N,K]^T )

@@ -176,3 +176,49 @@ def test_hf_live_if_available():
            logged_tol=3e-3, gnorm_tol=2e-3)  # perturbed state
     # and the checkpoint written by our model loads into HF strictly (compute_embeddings_videomae.py:56-69)
     hf.load_state_dict({k: v.cpu() for k, v in model.state_dict().items()}, strict=True)
+
+
+def test_uint8_input_path_is_bit_identical():
+    """uint8 clips + in-kernel ToTensor / Normalize(0.5, 0.25) (homeview.py:218-231) against the same clips normalised
+    on the host with torch in torchvision's operation order: patches, targets and therefore loss and gradients are
+    bit-identical."""
+    import bvc_b200 as bvc
+    from bvc_b200 import _lib as L
+    from tests.helpers import bvc_config
+    dev = torch.device("cuda:0")
+    cfg = O.make_config("tiny")
+    g = torch.Generator().manual_seed(11)
+    B = 3
+    u8 = torch.randint(0, 256, (B, cfg.num_frames, 3, cfg.image_size, cfg.image_size), generator=g, dtype=torch.uint8)
+    mean, std = (0.5, 0.5, 0.5), (0.25, 0.25, 0.25)
+    xf = u8.float().div(255)
+    xf = (xf - torch.tensor(mean).view(1, 1, 3, 1, 1)) / torch.tensor(std).view(1, 1, 3, 1, 1)
+    np.random.seed(4)
+    mask = O.batch_tube_masks(B, cfg.grid, 0.5).to(dev)
+    # kernel level: both outputs bit-equal
+    N = mask.shape[1]
+    nv = int((~mask[0]).sum())
+    vis = torch.zeros(B, nv, device=dev, dtype=torch.int32)
+    msk = torch.zeros(B, N - nv, device=dev, dtype=torch.int32)
+    slot = torch.zeros(B, N, device=dev, dtype=torch.int32)
+    status = torch.zeros(1, device=dev, dtype=torch.int32)
+    L.mask_to_index(mask.view(torch.uint8), nv, vis, msk, slot, status)
+    K = 3 * cfg.tubelet_size * cfg.patch_size ** 2
+    outs = []
+    for x, pn in ((xf.to(dev), None), (u8.to(dev), (mean, std))):
+        pv = torch.zeros(B * nv, K, device=dev, dtype=torch.bfloat16)
+        tg = torch.zeros(B * (N - nv), K, device=dev)
+        L.patchify_target(x, slot, cfg.tubelet_size, cfg.patch_size, nv, pv, tg, True, pixel_norm=pn)
+        outs.append((pv, tg))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    # model level
+    params = O.init_params(cfg, seed=1, perturb=True)
+    model = bvc.VideoMAEForPreTraining(bvc_config(cfg))
+    model.load_state_dict(params, strict=True)
+    model = model.to(dev).train()
+    with pytest.raises(ValueError):
+        model(u8.to(dev), bool_masked_pos=mask)
+    la = model(xf.to(dev), bool_masked_pos=mask).loss
+    model.set_input_normalization(mean, std)
+    lb = model(u8.to(dev), bool_masked_pos=mask).loss
+    assert float(la) == float(lb)

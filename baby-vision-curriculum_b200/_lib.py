@@ -12,7 +12,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libbvc.so")
-ABI_VERSION = 9
+ABI_VERSION = 10
 
 _lib = None
 
@@ -32,7 +32,7 @@ class GemmArgs(C.Structure):
         ("act", C.c_int32), ("aux_out", C.c_void_p), ("aux_in", C.c_void_p), ("ld_aux", C.c_int64),
         ("res", C.c_void_p), ("ldr", C.c_int64), ("res_idx", C.c_void_p),
         ("target", C.c_void_p), ("ldt", C.c_int64), ("loss_partial", C.c_void_p), ("logits_out", C.c_void_p),
-        ("colsum", C.c_void_p), ("block_n", C.c_int32),
+        ("colsum", C.c_void_p), ("block_n", C.c_int32), ("cta_pair", C.c_int32),
     ]
 
 
@@ -202,7 +202,7 @@ def patchify_target(pixels, slot, ts, ps, nv, patches_vis, target, norm_pix=True
 def gemm(a, b, M, N, K, *, lda=None, ldb=None, a_mn=False, b_mn=False, out_f32=None, out_bf16=None, ldo=None,
          out_seg=0, out_seg_stride=0, out_seg_off=0, alpha=1.0, alpha_dev=None, bias=None, act=0, aux_out=None,
          aux_in=None, ld_aux=0, res=None, ldr=0, res_idx=None, target=None, ldt=0, loss_partial=None,
-         logits_out=None, k_splits=1, block_n=0, colsum=None):
+         logits_out=None, k_splits=1, block_n=0, colsum=None, cta_pair=0):
     """out = epilogue(alpha * A . B^T); see include/bvc.h bvc_gemm_bf16 for the epilogue order."""
     _cuda(a, b, out_f32, out_bf16)
     g = GemmArgs()
@@ -230,6 +230,7 @@ def gemm(a, b, M, N, K, *, lda=None, ldb=None, a_mn=False, b_mn=False, out_f32=N
     g.loss_partial = loss_partial.data_ptr() if loss_partial is not None else None
     g.logits_out = logits_out.data_ptr() if logits_out is not None else None
     g.block_n = block_n
+    g.cta_pair = cta_pair
     g.colsum = colsum.data_ptr() if colsum is not None else None
     detail = ""
     if _prof is not None:

@@ -26,6 +26,20 @@ int gemm_launch_bn64(const bvc_gemm_args* a, int epi, cudaStream_t s);
 int gemm_launch_bn128(const bvc_gemm_args* a, int epi, cudaStream_t s);
 int gemm_launch_bn192(const bvc_gemm_args* a, int epi, cudaStream_t s);
 int gemm_launch_bn256(const bvc_gemm_args* a, int epi, cudaStream_t s);
+int gemm_launch_pair128(const bvc_gemm_args* a, int epi, cudaStream_t s);
+int gemm_launch_pair192(const bvc_gemm_args* a, int epi, cudaStream_t s);
+int gemm_launch_pair256(const bvc_gemm_args* a, int epi, cudaStream_t s);
+
+// CTA-pair (cta_group::2, 256 x BN) tiles exist for BN = 128 / 256, and for BN = 192 when B is K-major (each CTA
+// stages BN / 2 rows of B: whole 64-element swizzle atoms when B is MN-major)
+static bool pair_supported(int bn, int b_mn_major) { return bn == 128 || bn == 256 || (bn == 192 && !b_mn_major); }
+
+// cta_pair == 0: choose.  Measured on B200 (tools/gpu_gemm_tune.py): see pick_pair_auto below.
+static bool pick_pair_auto(const bvc_gemm_args* a, int bn) {
+  (void)a;
+  (void)bn;
+  return false;
+}
 
 static int pick_block_n(int M, int N, int K, bool wgrad) {
   // measured on B200 over every shape of the ViT-B step (tools/gpu_gemm_tune.py, profiles/r01_gemm_tune.log)
@@ -94,6 +108,7 @@ extern "C" int bvc_gemm_bf16(const bvc_gemm_args* a, void* stream) {
   BVC_CHECK_ARG(a->M > 0 && a->N > 0 && a->K > 0);
   BVC_CHECK_ARG(a->N % 8 == 0 && a->lda % 8 == 0 && a->ldb % 8 == 0 && a->ldo % 8 == 0);
   BVC_CHECK_ARG(a->block_n == 0 || a->block_n == 64 || a->block_n == 128 || a->block_n == 192 || a->block_n == 256);
+  BVC_CHECK_ARG(a->cta_pair >= 0 && a->cta_pair <= 2);
   BVC_CHECK_ARG(a->out_f32 != nullptr || a->out_bf16 != nullptr);
   BVC_CHECK_ARG((((uintptr_t)a->a) & 15) == 0 && (((uintptr_t)a->b) & 15) == 0);
   BVC_CHECK_ARG(a->act == 0 || a->act == 1 || (a->act == 2 && a->aux_in != nullptr));
@@ -107,6 +122,9 @@ extern "C" int bvc_gemm_bf16(const bvc_gemm_args* a, void* stream) {
   // loss GEMMs resolve the tile width exactly like bvc_gemm_loss_slots() (which does not know K)
   const int bn = a->target ? resolve_block_n(a->M, a->N, a->block_n)
                            : resolve_block_n(a->M, a->N, a->block_n, a->K, a->a_mn_major && a->b_mn_major);
+  const bool pair = bvc::pair_supported(bn, a->b_mn_major) &&
+                    (a->cta_pair == 2 || (a->cta_pair == 0 && bvc::pick_pair_auto(a, bn)));
+  BVC_CHECK_ARG(a->cta_pair != 2 || pair);
   // pick the leanest epilogue variant that covers the request (gemm_kernel.cuh); anything unusual -> generic
   int epi = bvc::EPI_GENERIC;
   const bool seg = a->out_seg > 0;
@@ -114,8 +132,9 @@ extern "C" int bvc_gemm_bf16(const bvc_gemm_args* a, void* stream) {
     const int kb_total = (a->K + bvc::BK - 1) / bvc::BK;
     int ks = a->k_splits;
     if (ks <= 0) {  // mirror of resolve_k_splits(): only the "is it > 1" answer is needed here
-      const long long tiles = (long long)((a->M + bvc::BM - 1) / bvc::BM) * ((a->N + bn - 1) / bn);
-      ks = (int)((2LL * bvc::num_sms() + tiles - 1) / tiles);
+      const int tile_m = pair ? 2 * bvc::BM : bvc::BM, workers = pair ? bvc::num_sms() / 2 : bvc::num_sms();
+      const long long tiles = (long long)((a->M + tile_m - 1) / tile_m) * ((a->N + bn - 1) / bn);
+      ks = (int)((2LL * workers + tiles - 1) / tiles);
       if (ks > kb_total / 4) ks = kb_total / 4 > 0 ? kb_total / 4 : 1;
     }
     if (ks > kb_total) ks = kb_total;
@@ -134,6 +153,13 @@ extern "C" int bvc_gemm_bf16(const bvc_gemm_args* a, void* stream) {
       epi = bvc::EPI_RES;
     else if (a->act == 0 && !a->res && !a->target && !seg && a->out_bf16 && !a->out_f32)
       epi = bvc::EPI_PLAIN;
+  }
+  if (pair) {
+    switch (bn) {
+      case 256: return bvc::gemm_launch_pair256(a, epi, s);
+      case 192: return bvc::gemm_launch_pair192(a, epi, s);
+      default: return bvc::gemm_launch_pair128(a, epi, s);
+    }
   }
   switch (bn) {
     case 256: return bvc::gemm_launch_bn256(a, epi, s);

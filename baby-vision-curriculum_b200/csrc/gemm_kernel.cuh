@@ -42,12 +42,19 @@ struct GemmParams {
   int has_pre;  // tma_pre describes the epilogue's global operand (residual / target / GELU pre-activation)
 };
 
-template <int BN>
+// PAIR = 1: the kernel runs as clusters of two CTAs (the two SMs of a TPC) on 256 x BN output tiles with
+// tcgen05.mma.cta_group::2: each CTA stages its own 128 rows of A and HALF (BN / 2 rows) of the B tile and owns the
+// accumulator of its 128 rows; see the protocol notes in bvc_ptx.cuh.  Per 128 x BN x 64 of MMA work an SM then pulls
+// 16 + BN / 8 KB through the L2 -> SM fabric instead of 16 + BN / 4 KB, which is what capped the one-CTA tiles near
+// 1050 TFLOP/s.
+template <int BN, int PAIR = 0>
 struct GemmCfg {
   static constexpr int kABytes = BM * BK * 2;
-  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kBRows = PAIR ? BN / 2 : BN;   // B rows staged by one CTA
+  static constexpr int kBBytes = kBRows * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BN == 256) ? 4 : (BN == 192) ? 4 : (BN == 128) ? 6 : 8;
+  static constexpr int kStages = PAIR ? ((BN == 256) ? 6 : (BN == 192) ? 6 : 8)
+                                      : ((BN == 256) ? 4 : (BN == 192) ? 4 : (BN == 128) ? 6 : 8);
   static constexpr int kTmemCols = (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
   static constexpr int kStagingBytes = kEpiWarps * 4096;  // per epilogue warp: 32 rows x 32 fp32, 128B-swizzled
   static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/;
@@ -137,11 +144,18 @@ __device__ __forceinline__ uint32_t f32x2_to_bf16x2(uint64_t v) {
   return pack_bf16x2(a, b);
 }
 
-template <int BN, int A_MN, int B_MN, int EPI>
+template <int BN, int A_MN, int B_MN, int EPI, int PAIR>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
             const __grid_constant__ CUtensorMap tma_pre, const __grid_constant__ GemmParams p) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, PAIR>;
+  static_assert(!PAIR || (Cfg::kBRows % (B_MN ? 64 : 8) == 0), "pair tile: B half must be whole swizzle atoms");
+  // pair mode: rank of this CTA in its cluster (0 = leader: owns the full barriers and issues the MMAs); the cluster
+  // (not the CTA) is the persistent worker
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  const int worker = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int n_workers = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  constexpr int kTileM = PAIR ? 2 * BM : BM;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* staging = smem + Cfg::kStages * Cfg::kStageBytes;
@@ -163,13 +177,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], kEpiWarps);
+      mbar_init(&tmem_empty[i], PAIR ? 2 * kEpiWarps : kEpiWarps);  // pair: the epilogue warps of both CTAs
     }
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
+  if (warp == 1) {
+    if (PAIR) tmem_alloc_pair(tmem_slot, Cfg::kTmemCols);
+    else tmem_alloc(tmem_slot, Cfg::kTmemCols);
+  }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();  // the peer's barriers are initialised before anything is signalled on them
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -179,11 +197,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+      for (int w = worker; w < total_work; w += n_workers) {
         const int split = w % p.k_splits;
         const int tile = w / p.k_splits;
-        const int m0 = (tile / p.tiles_n) * BM;
+        const int m0 = (tile / p.tiles_n) * kTileM + (int)rank * BM;
         const int n0 = (tile % p.tiles_n) * BN;
+        const int nb0 = n0 + (int)rank * Cfg::kBRows;  // first B row this CTA stages
         const int kb0 = split * p.kb_per_split;
         const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
         // pull this tile's epilogue operand into L2 while its MMAs run: the epilogue's loads then see L2 latency,
@@ -197,18 +216,39 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
           mbar_wait(&empty_bar[stage], phase ^ 1u);
           uint8_t* sa = smem + stage * Cfg::kStageBytes;
           uint8_t* sb = sa + Cfg::kABytes;
-          mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-          if (A_MN == 0) {
-            tma_load_2d(sa, &tma_a, &full_bar[stage], kb * BK, m0);
-          } else {
+          if (PAIR) {
+            // both CTAs' bytes land on the leader's barrier; the leader arms it for the pair
+            if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
+            const uint32_t lbar = mapa_shared(smem_u32(&full_bar[stage]), 0);
+            if (A_MN == 0) {
+              tma_load_2d_pair(sa, &tma_a, lbar, kb * BK, m0);
+            } else {
 #pragma unroll
-            for (int j = 0; j < BM / 64; ++j) tma_load_2d(sa + j * 8192, &tma_a, &full_bar[stage], m0 + j * 64, kb * BK);
-          }
-          if (B_MN == 0) {
-            tma_load_2d(sb, &tma_b, &full_bar[stage], kb * BK, n0);
-          } else {
+              for (int j = 0; j < BM / 64; ++j) tma_load_2d_pair(sa + j * 8192, &tma_a, lbar, m0 + j * 64, kb * BK);
+            }
+            if (B_MN == 0) {
+              tma_load_2d_pair(sb, &tma_b, lbar, kb * BK, nb0);
+            } else {
 #pragma unroll
-            for (int j = 0; j < BN / 64; ++j) tma_load_2d(sb + j * 8192, &tma_b, &full_bar[stage], n0 + j * 64, kb * BK);
+              for (int j = 0; j < Cfg::kBRows / 64; ++j)
+                tma_load_2d_pair(sb + j * 8192, &tma_b, lbar, nb0 + j * 64, kb * BK);
+            }
+          } else {
+            mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+            if (A_MN == 0) {
+              tma_load_2d(sa, &tma_a, &full_bar[stage], kb * BK, m0);
+            } else {
+#pragma unroll
+              for (int j = 0; j < BM / 64; ++j)
+                tma_load_2d(sa + j * 8192, &tma_a, &full_bar[stage], m0 + j * 64, kb * BK);
+            }
+            if (B_MN == 0) {
+              tma_load_2d(sb, &tma_b, &full_bar[stage], kb * BK, n0);
+            } else {
+#pragma unroll
+              for (int j = 0; j < BN / 64; ++j)
+                tma_load_2d(sb + j * 8192, &tma_b, &full_bar[stage], n0 + j * 64, kb * BK);
+            }
           }
           if (++stage == Cfg::kStages) {
             stage = 0;
@@ -222,14 +262,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     // the tcgen05 instructions.  (With the entire loop under `if (lane == 0)` ptxas kept the loop state in vector
     // registers and spent ~16 instructions -- R2UR moves, descriptor re-masking, an ELECT retry loop -- per MMA,
     // more than a 128 x N x 16 MMA takes to execute for N <= 192.)
-    constexpr uint32_t idesc = umma_idesc_bf16(BN, A_MN, B_MN, BM);
+    constexpr uint32_t idesc = umma_idesc_bf16(BN, A_MN, B_MN, kTileM);
     // descriptor start-address step of one K = 16 slice, in 16-byte units: 2048 B (MN-major) or 32 B (K-major)
     constexpr uint64_t kStepA = A_MN ? 128 : 2, kStepB = B_MN ? 128 : 2;
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+    // pair mode: only the leader CTA issues (its MMAs drive the tensor cores of both SMs); the peer's warp 1 just
+    // holds the TMEM allocation
+    for (int w = (PAIR && rank != 0) ? total_work : worker; w < total_work; w += n_workers) {
       const int split = w % p.k_splits;
       const int kb0 = split * p.kb_per_split;
       const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
@@ -245,11 +287,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
           const uint64_t da = A_MN ? umma_smem_desc(a_addr, 1024, 8192) : umma_smem_desc(a_addr, 1024, 16);
           const uint64_t db = B_MN ? umma_smem_desc(b_addr, 1024, 8192) : umma_smem_desc(b_addr, 1024, 16);
           const uint32_t acc0 = kb > kb0;
+          if (PAIR) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k)
-            umma_bf16_ss(d_tmem, da + kStepA * k, db + kStepB * k, idesc, acc0 | (k > 0));
-          umma_commit(&empty_bar[stage]);
-          if (kb + 1 == kb1) umma_commit(&tmem_full[acc]);
+            for (int k = 0; k < BK / 16; ++k)
+              umma_bf16_ss_pair(d_tmem, da + kStepA * k, db + kStepB * k, idesc, acc0 | (k > 0));
+            umma_commit_pair(&empty_bar[stage]);  // frees the stage in both CTAs
+            if (kb + 1 == kb1) umma_commit_pair(&tmem_full[acc]);
+          } else {
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k)
+              umma_bf16_ss(d_tmem, da + kStepA * k, db + kStepB * k, idesc, acc0 | (k > 0));
+            umma_commit(&empty_bar[stage]);
+            if (kb + 1 == kb1) umma_commit(&tmem_full[acc]);
+          }
         }
         __syncwarp();
         if (++stage == Cfg::kStages) {
@@ -258,7 +308,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         }
       }
       if (kb0 >= kb1) {  // empty K range (never produced by the host-side split choice): keep the protocol alive
-        if (elect_one()) umma_commit(&tmem_full[acc]);
+        if (elect_one()) {
+          if (PAIR) umma_commit_pair(&tmem_full[acc]);
+          else umma_commit(&tmem_full[acc]);
+        }
         __syncwarp();
       }
       acc ^= 1;
@@ -291,9 +344,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                                                          EPI == EPI_LOSS);
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+    // pair mode: both CTAs hand their accumulator stage back to the leader's MMA warp
+    const uint32_t tmem_empty_leader0 = PAIR ? mapa_shared(smem_u32(&tmem_empty[0]), 0) : 0u;
+    const uint32_t tmem_empty_leader1 = PAIR ? mapa_shared(smem_u32(&tmem_empty[1]), 0) : 0u;
+    for (int w = worker; w < total_work; w += n_workers) {
       const int tile = w / p.k_splits;
-      const int m0 = (tile / p.tiles_n) * BM;
+      const int m0 = (tile / p.tiles_n) * kTileM + (int)rank * BM;
       const int n0 = (tile % p.tiles_n) * BN;
       const int rbase = m0 + q * 32;
       const bool interior = m0 + BM <= p.M && n0 + BN <= p.N;  // warp-uniform
@@ -337,7 +393,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         if (cc + 32 >= kColsPerWarp) {  // last chunk of this tile is in registers: hand the accumulator back
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+          if (lane == 0) {
+            if (PAIR) mbar_arrive_cluster(acc ? tmem_empty_leader1 : tmem_empty_leader0);
+            else mbar_arrive(&tmem_empty[acc]);
+          }
         }
 #pragma unroll
         for (int c = 0; c < 8; ++c)
@@ -566,7 +625,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       }
       if (kLoss && p.loss_partial) {
         lsum = warp_sum(lsum);
-        if (lane == 0) p.loss_partial[(long long)tile * kEpiWarps + e] = lsum;
+        // slot = (128-row tile index) * tiles_n + column tile (pair mode: a CTA whose rows are all past M has none)
+        if (lane == 0 && m0 < p.M)
+          p.loss_partial[((long long)(m0 / BM) * p.tiles_n + tile % p.tiles_n) * kEpiWarps + e] = lsum;
       }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
@@ -574,19 +635,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();  // the peer may still read this CTA's B half / signal its barriers until here
+  else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+    if (PAIR) tmem_dealloc_pair(tmem_base, Cfg::kTmemCols);
+    else tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
 }
 
 // k-split resolution shared by the host dispatcher (it decides the epilogue variant) and the launcher
-static inline void resolve_k_splits(const bvc_gemm_args* a, int bn, int* kb_per_split, int* k_splits) {
-  const int tiles_m = (a->M + BM - 1) / BM, tiles_n = (a->N + bn - 1) / bn;
+static inline void resolve_k_splits(const bvc_gemm_args* a, int bn, int pair, int* kb_per_split, int* k_splits) {
+  const int tile_m = pair ? 2 * BM : BM;
+  const int tiles_m = (a->M + tile_m - 1) / tile_m, tiles_n = (a->N + bn - 1) / bn;
   const int kb_total = (a->K + BK - 1) / BK;
   int ks = a->k_splits;
-  const int sms = num_sms();
+  const int sms = pair ? num_sms() / 2 : num_sms();  // persistent workers: CTAs, or CTA pairs
   if (ks <= 0) {
     const long long tiles = (long long)tiles_m * tiles_n;
     ks = (int)((2LL * sms + tiles - 1) / tiles);  // ~2 waves of work items
@@ -598,16 +662,38 @@ static inline void resolve_k_splits(const bvc_gemm_args* a, int bn, int* kb_per_
   *k_splits = (kb_total + *kb_per_split - 1) / *kb_per_split;
 }
 
-template <int BN, int A_MN, int B_MN, int EPI>
+template <int BN, int A_MN, int B_MN, int EPI, int PAIR = 0>
 static int launch_gemm(const bvc_gemm_args* a, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, PAIR>;
+  static_assert(Cfg::kSmemBytes <= 232448, "stage ring does not fit the 227 KB of shared memory");
   static bool attr_done = false;
+  static int max_workers = 0;  // co-resident CTAs (pair mode: clusters)
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_kernel<BN, A_MN, B_MN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         Cfg::kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(gemm_kernel<BN, A_MN, B_MN, EPI, PAIR>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     if (e != cudaSuccess) {
       fprintf(stderr, "bvc: cudaFuncSetAttribute(gemm) failed: %s\n", cudaGetErrorString(e));
       return BVC_ERR_LAUNCH;
+    }
+    max_workers = PAIR ? num_sms() / 2 : num_sms();
+    if (PAIR) {
+      // how many CTA pairs the device can hold at once (GPCs with an odd number of usable SMs lose one)
+      cudaLaunchConfig_t qc = {};
+      qc.gridDim = dim3(2 * (num_sms() / 2));
+      qc.blockDim = dim3(kGemmThreads);
+      qc.dynamicSmemBytes = Cfg::kSmemBytes;
+      cudaLaunchAttribute qa[1];
+      qa[0].id = cudaLaunchAttributeClusterDimension;
+      qa[0].val.clusterDim.x = 2;
+      qa[0].val.clusterDim.y = 1;
+      qa[0].val.clusterDim.z = 1;
+      qc.attrs = qa;
+      qc.numAttrs = 1;
+      int n_clusters = 0;
+      if (cudaOccupancyMaxActiveClusters(&n_clusters, gemm_kernel<BN, A_MN, B_MN, EPI, PAIR>, &qc) == cudaSuccess &&
+          n_clusters > 0 && n_clusters < max_workers)
+        max_workers = n_clusters;
+      (void)cudaGetLastError();
     }
     attr_done = true;
   }
@@ -624,7 +710,7 @@ static int launch_gemm(const bvc_gemm_args* a, cudaStream_t stream) {
     int rc = make_tmap(&ta, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a->a, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
     if (B_MN == 0) {
-      dims[0] = (uint64_t)a->K; dims[1] = (uint64_t)a->N; box[0] = BK; box[1] = BN;
+      dims[0] = (uint64_t)a->K; dims[1] = (uint64_t)a->N; box[0] = BK; box[1] = Cfg::kBRows;
     } else {
       dims[0] = (uint64_t)a->N; dims[1] = (uint64_t)a->K; box[0] = 64; box[1] = BK;
     }
@@ -651,10 +737,11 @@ static int launch_gemm(const bvc_gemm_args* a, cudaStream_t stream) {
   GemmParams p;
   p.has_pre = has_pre;
   p.M = a->M; p.N = a->N; p.K = a->K;
-  p.tiles_m = (a->M + BM - 1) / BM;
+  constexpr int kTileM = PAIR ? 2 * BM : BM;
+  p.tiles_m = (a->M + kTileM - 1) / kTileM;
   p.tiles_n = (a->N + BN - 1) / BN;
   p.kb_total = (a->K + BK - 1) / BK;
-  resolve_k_splits(a, BN, &p.kb_per_split, &p.k_splits);
+  resolve_k_splits(a, BN, PAIR, &p.kb_per_split, &p.k_splits);
   p.out_f32 = a->out_f32; p.out_bf16 = (bf16*)a->out_bf16; p.ldo = a->ldo;
   p.out_seg = a->out_seg; p.out_seg_stride = a->out_seg_stride; p.out_seg_off = a->out_seg_off;
   p.alpha = a->alpha_host; p.alpha_dev = a->alpha_dev; p.bias = a->bias; p.act = a->act;
@@ -667,39 +754,67 @@ static int launch_gemm(const bvc_gemm_args* a, cudaStream_t stream) {
                   a->res == nullptr && a->target == nullptr);
   }
   const long long total = (long long)p.tiles_m * p.tiles_n * p.k_splits;
-  const int sms = num_sms();
-  const int grid = (int)(total < sms ? total : sms);
-  gemm_kernel<BN, A_MN, B_MN, EPI><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, tp, p);
+  const int workers = (int)(total < max_workers ? total : max_workers);
+  if constexpr (PAIR != 0) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * workers);
+    cfg.blockDim = dim3(kGemmThreads);
+    cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (cudaLaunchKernelEx(&cfg, gemm_kernel<BN, A_MN, B_MN, EPI, PAIR>, ta, tb, tp, p) != cudaSuccess) {
+      fprintf(stderr, "bvc: pair GEMM launch failed: %s\n", cudaGetErrorString(cudaGetLastError()));
+      return BVC_ERR_LAUNCH;
+    }
+  } else {
+    gemm_kernel<BN, A_MN, B_MN, EPI, PAIR><<<workers, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, tp, p);
+  }
   BVC_CHECK_LAUNCH();
   return BVC_OK;
 }
 
 // every (operand-major, epilogue) combination the model uses gets its own lean kernel; anything else runs the
-// generic (all-runtime-flags) epilogue
-template <int BN>
-static int gemm_dispatch_bn(const bvc_gemm_args* a, int epi, cudaStream_t s) {
+// generic (all-runtime-flags) epilogue.  PAIR variants exist for the tile widths whose B half is a whole number of
+// swizzle atoms (BN = 128, 256; BN = 192 only with a K-major B).
+template <int BN, int PAIR>
+static int gemm_dispatch_bn_pair(const bvc_gemm_args* a, int epi, cudaStream_t s) {
   const int am = a->a_mn_major, bm = a->b_mn_major;
   if (am == 0 && bm == 0) {
     switch (epi) {
-      case EPI_PLAIN: return launch_gemm<BN, 0, 0, EPI_PLAIN>(a, s);
-      case EPI_GELU: return launch_gemm<BN, 0, 0, EPI_GELU>(a, s);
-      case EPI_RES: return launch_gemm<BN, 0, 0, EPI_RES>(a, s);
-      case EPI_LOSS: return launch_gemm<BN, 0, 0, EPI_LOSS>(a, s);
-      default: return launch_gemm<BN, 0, 0, EPI_GENERIC>(a, s);
+      case EPI_PLAIN: return launch_gemm<BN, 0, 0, EPI_PLAIN, PAIR>(a, s);
+      case EPI_GELU: return launch_gemm<BN, 0, 0, EPI_GELU, PAIR>(a, s);
+      case EPI_RES: return launch_gemm<BN, 0, 0, EPI_RES, PAIR>(a, s);
+      case EPI_LOSS: return launch_gemm<BN, 0, 0, EPI_LOSS, PAIR>(a, s);
+      default: return launch_gemm<BN, 0, 0, EPI_GENERIC, PAIR>(a, s);
     }
   }
-  if (am == 0 && bm == 1) {
-    switch (epi) {
-      case EPI_PLAIN: return launch_gemm<BN, 0, 1, EPI_PLAIN>(a, s);
-      case EPI_DGELU: return launch_gemm<BN, 0, 1, EPI_DGELU>(a, s);
-      default: return launch_gemm<BN, 0, 1, EPI_GENERIC>(a, s);
+  if constexpr (!PAIR || (BN / 2) % 64 == 0) {
+    if (am == 0 && bm == 1) {
+      switch (epi) {
+        case EPI_PLAIN: return launch_gemm<BN, 0, 1, EPI_PLAIN, PAIR>(a, s);
+        case EPI_DGELU: return launch_gemm<BN, 0, 1, EPI_DGELU, PAIR>(a, s);
+        default: return launch_gemm<BN, 0, 1, EPI_GENERIC, PAIR>(a, s);
+      }
     }
+    if (am == 1 && bm == 1) {
+      if (epi == EPI_SPLITK) return launch_gemm<BN, 1, 1, EPI_SPLITK, PAIR>(a, s);
+      return launch_gemm<BN, 1, 1, EPI_GENERIC, PAIR>(a, s);
+    }
+  } else {
+    if (bm == 1) return BVC_ERR_ARG;  // resolved away by the host dispatcher (gemm.cu: pair_supported)
   }
-  if (am == 1 && bm == 1) {
-    if (epi == EPI_SPLITK) return launch_gemm<BN, 1, 1, EPI_SPLITK>(a, s);
-    return launch_gemm<BN, 1, 1, EPI_GENERIC>(a, s);
-  }
-  return launch_gemm<BN, 1, 0, EPI_GENERIC>(a, s);
+  return launch_gemm<BN, 1, 0, EPI_GENERIC, PAIR>(a, s);
+}
+
+template <int BN>
+static int gemm_dispatch_bn(const bvc_gemm_args* a, int epi, cudaStream_t s) {
+  return gemm_dispatch_bn_pair<BN, 0>(a, epi, s);
 }
 
 }  // namespace bvc

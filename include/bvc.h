@@ -28,7 +28,7 @@ extern "C" {
 #define BVC_ERR_ARG (-1)
 #define BVC_ERR_DRIVER (-2)
 #define BVC_ERR_LAUNCH (-3)
-#define BVC_ABI_VERSION 9
+#define BVC_ABI_VERSION 10
 
 /* library / build info: returns BVC_ABI_VERSION (bumped when a signature changes) */
 int bvc_abi_version(void);
@@ -120,6 +120,8 @@ typedef struct bvc_gemm_args {
   void* logits_out;       /* bf16, ld = ldo */
   float* colsum;          /* fp32 [N] or null */
   int32_t block_n;        /* 0 = choose; else 64 / 128 / 192 / 256 */
+  int32_t cta_pair;       /* 0 = choose; 1 = one CTA per 128 x block_n tile; 2 = CTA pair (tcgen05 cta_group::2) on
+                             256 x block_n tiles (block_n 128 / 256, or 192 with a K-major B; else BVC_ERR_ARG) */
 } bvc_gemm_args;
 
 int bvc_gemm_bf16(const bvc_gemm_args* args, void* stream);

@@ -28,10 +28,10 @@ SHAPES = [
 ]
 
 
-def run_case(M, N, K, a_mn, b_mn, mode, bn, ks=0):
+def run_case(M, N, K, a_mn, b_mn, mode, bn, ks=0, pair=1):
     A = torch.randn(K if a_mn else M, M if a_mn else K, device=dev).to(torch.bfloat16)
     B = (torch.randn(K if b_mn else N, N if b_mn else K, device=dev) * 0.05).to(torch.bfloat16)
-    kw = dict(a_mn=bool(a_mn), b_mn=bool(b_mn), block_n=bn)
+    kw = dict(a_mn=bool(a_mn), b_mn=bool(b_mn), block_n=bn, cta_pair=pair)
     if mode == "wgrad":
         of = torch.zeros(M, N, device=dev)
         fn = lambda: L.gemm(A, B, M, N, K, out_f32=of, k_splits=ks, **kw)  # noqa: E731
@@ -78,11 +78,16 @@ for sh in SHAPES:
     res = {}
     for bn in (64, 128, 192, 256):
         try:
-            res[bn] = run_case(M, N, K, a_mn, b_mn, mode, bn)
+            res[f"bn{bn}"] = run_case(M, N, K, a_mn, b_mn, mode, bn)
         except Exception as ex:  # noqa: BLE001
-            res[bn] = float("inf")
+            res[f"bn{bn}"] = float("inf")
+    for bn in (128, 192, 256):  # CTA-pair (cta_group::2) tiles, 256 x bn
+        try:
+            res[f"p{bn}"] = run_case(M, N, K, a_mn, b_mn, mode, bn, pair=2)
+        except Exception as ex:  # noqa: BLE001
+            res[f"p{bn}"] = float("inf")
     best = min(res, key=res.get)
-    auto = run_case(M, N, K, a_mn, b_mn, mode, 0)
+    auto = run_case(M, N, K, a_mn, b_mn, mode, 0, pair=0)
     print(f"TUNE M{M} N{N} K{K} {'T' if a_mn else 'N'}{'T' if b_mn else 'N'} {mode:6s} " +
-          " ".join(f"bn{b}={t*1e3:7.1f}" for b, t in res.items()) +
-          f" | auto={auto*1e3:7.1f} best=bn{best} {2*M*N*K/res[best]/1e9:6.0f} TF/s", flush=True)
+          " ".join(f"{b}={t*1e3:6.1f}" for b, t in res.items()) +
+          f" | auto={auto*1e3:6.1f} best={best} {2*M*N*K/res[best]/1e9:6.0f} TF/s", flush=True)

@@ -49,15 +49,15 @@ def bf(t):
 
 # ------------------------------------------------------------------------------------------------ GEMM
 @guarded
-def gemm_case(M, N, K, a_mn, b_mn, bn, mode="plain", ks=1):
+def gemm_case(M, N, K, a_mn, b_mn, bn, mode="plain", ks=1, pair=0):
     g = torch.Generator(device=dev).manual_seed(M * 7 + N * 3 + K + a_mn * 2 + b_mn)
     A = bf(torch.randn(M, K, device=dev, generator=g))
     Bm = bf(torch.randn(N, K, device=dev, generator=g) * 0.5)
     a_store = A.t().contiguous() if a_mn else A
     b_store = Bm.t().contiguous() if b_mn else Bm
     ref = A.double() @ Bm.double().t()
-    name = f"gemm M{M} N{N} K{K} a_mn{a_mn} b_mn{b_mn} bn{bn} {mode} ks{ks}"
-    kw = dict(a_mn=bool(a_mn), b_mn=bool(b_mn), block_n=bn)
+    name = f"gemm M{M} N{N} K{K} a_mn{a_mn} b_mn{b_mn} bn{bn} {mode} ks{ks}" + (" pair" if pair == 2 else "")
+    kw = dict(a_mn=bool(a_mn), b_mn=bool(b_mn), block_n=bn, cta_pair=pair)
     if mode == "plain":
         of = torch.full((M, N), float("nan"), device=dev)
         ob = torch.zeros(M, N, device=dev, dtype=torch.bfloat16)
@@ -150,6 +150,30 @@ def run_gemm_epilogues():
     gemm_case(300, 384, 128, 0, 0, 0, "residual_idx_seg")
     gemm_case(300, 1536, 384, 0, 0, 0, "loss")
     gemm_case(2816, 1536, 384, 0, 0, 256, "loss")
+
+
+def run_gemm_pair():
+    """CTA-pair (cta_group::2, 256 x BN) tiles: every operand major, every fused epilogue, ragged edges (a pair whose
+    second CTA lies entirely past M), multi-tile persistence and split-K."""
+    gemm_case(256, 256, 64, 0, 0, 256, pair=2)
+    gemm_case(256, 128, 256, 0, 0, 128, pair=2)
+    gemm_case(512, 384, 192, 0, 0, 192, pair=2)
+    for a_mn, b_mn in ((0, 0), (0, 1), (1, 0), (1, 1)):
+        gemm_case(200, 136, 72, a_mn, b_mn, 128, pair=2)     # ragged M / N / K tails
+        gemm_case(384, 512, 200, a_mn, b_mn, 256, pair=2)    # second CTA of the last pair is past M
+        gemm_case(1000, 768, 1536, a_mn, b_mn, 256, pair=2)
+        gemm_case(40000, 768, 512, a_mn, b_mn, 256, pair=2)  # several tiles per cluster (both accumulator stages)
+    gemm_case(1000, 768, 1536, 0, 0, 192, pair=2)
+    gemm_case(768, 1536, 4096, 1, 1, 256, "splitk", 0, pair=2)
+    gemm_case(384, 1152, 2048, 1, 1, 128, "splitk", 5, pair=2)
+    for bn in (128, 192, 256):
+        gemm_case(300, 3 * bn, 256, 0, 0, bn, "bias_gelu", pair=2)
+        gemm_case(2560, 3 * bn, 256, 0, 0, bn, "bias_gelu", pair=2)
+    gemm_case(2560, 512, 256, 0, 1, 256, "gelu_bwd", pair=2)
+    gemm_case(2560, 512, 256, 0, 0, 256, "residual", pair=2)
+    gemm_case(300, 384, 128, 0, 0, 128, "residual_idx_seg", pair=2)
+    gemm_case(300, 1536, 384, 0, 0, 256, "loss", pair=2)
+    gemm_case(2816, 1536, 384, 0, 0, 256, "loss", pair=2)
 
 
 # ------------------------------------------------------------------------------------------------ rows
@@ -405,7 +429,7 @@ if __name__ == "__main__":
     for w in which:
         {"gemm00": lambda: run_gemm_major(0, 0), "gemm01": lambda: run_gemm_major(0, 1),
          "gemm10": lambda: run_gemm_major(1, 0), "gemm11": lambda: run_gemm_major(1, 1),
-         "gemmx": run_gemm_epilogues, "rows": run_rows, "patchify": run_patchify, "attn": run_attn, "perf": run_perf}[w]()
+         "gemmx": run_gemm_epilogues, "gemmpair": run_gemm_pair, "rows": run_rows, "patchify": run_patchify, "attn": run_attn, "perf": run_perf}[w]()
     torch.cuda.synchronize()
     nfail = sum(1 for _, ok in RESULTS if not ok)
     print(f"SELFTEST {len(RESULTS) - nfail}/{len(RESULTS)} passed in {time.time() - t0:.1f}s", flush=True)

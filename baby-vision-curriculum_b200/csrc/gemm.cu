@@ -34,12 +34,15 @@ int gemm_launch_pair256(const bvc_gemm_args* a, int epi, cudaStream_t s);
 // stages BN / 2 rows of B: whole 64-element swizzle atoms when B is MN-major)
 static bool pair_supported(int bn, int b_mn_major) { return bn == 128 || bn == 256 || (bn == 192 && !b_mn_major); }
 
-// cta_pair == 0: choose.  Measured on B200 (tools/gpu_gemm_tune.py): see pick_pair_auto below.
-static bool pick_pair_auto(const bvc_gemm_args* a, int bn) {
-  (void)a;
-  (void)bn;
-  return false;
+// cta_pair == 0: choose.  Measured on B200 over every shape of the ViT-B step (tools/gpu_gemm_tune.py,
+// profiles/r01_gemm_tune_pair.log): the pair tiles win 5-10 % on every contraction with K >= 1152 (mainloop-bound:
+// half the B traffic per flop) and lose on the short-K, epilogue-bound ones (a pair hands its accumulators back in
+// lockstep).  Tile width in pair mode: 256, except a residual epilogue on an N that is not a multiple of 256 (the
+// fp32 residual rows of the wasted columns cost more than the narrower tile).
+static bool pick_pair_auto(const bvc_gemm_args* a) {
+  return a->block_n == 0 && a->target == nullptr && a->K >= 1152 && a->N >= 256 && a->M >= 256;
 }
+static int pair_auto_block_n(const bvc_gemm_args* a) { return (a->N % 256 != 0 && a->res != nullptr) ? 128 : 256; }
 
 static int pick_block_n(int M, int N, int K, bool wgrad) {
   // measured on B200 over every shape of the ViT-B step (tools/gpu_gemm_tune.py, profiles/r01_gemm_tune.log)
@@ -120,11 +123,14 @@ extern "C" int bvc_gemm_bf16(const bvc_gemm_args* a, void* stream) {
   BVC_CHECK_ARG(a->b_mn_major == 0 ? a->ldb >= a->K : a->ldb >= a->N);
   cudaStream_t s = (cudaStream_t)stream;
   // loss GEMMs resolve the tile width exactly like bvc_gemm_loss_slots() (which does not know K)
-  const int bn = a->target ? resolve_block_n(a->M, a->N, a->block_n)
-                           : resolve_block_n(a->M, a->N, a->block_n, a->K, a->a_mn_major && a->b_mn_major);
-  const bool pair = bvc::pair_supported(bn, a->b_mn_major) &&
-                    (a->cta_pair == 2 || (a->cta_pair == 0 && bvc::pick_pair_auto(a, bn)));
-  BVC_CHECK_ARG(a->cta_pair != 2 || pair);
+  int bn = a->target ? resolve_block_n(a->M, a->N, a->block_n)
+                     : resolve_block_n(a->M, a->N, a->block_n, a->K, a->a_mn_major && a->b_mn_major);
+  bool pair = a->cta_pair == 2;
+  if (a->cta_pair == 0 && bvc::pick_pair_auto(a)) {
+    pair = true;
+    bn = bvc::pair_auto_block_n(a);
+  }
+  BVC_CHECK_ARG(!pair || bvc::pair_supported(bn, a->b_mn_major));
   // pick the leanest epilogue variant that covers the request (gemm_kernel.cuh); anything unusual -> generic
   int epi = bvc::EPI_GENERIC;
   const bool seg = a->out_seg > 0;

@@ -12,7 +12,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libbvc.so")
-ABI_VERSION = 10
+ABI_VERSION = 11
 
 _lib = None
 
@@ -76,6 +76,19 @@ _SIGNATURES = {
                                         C.c_float, C.c_void_p, C.c_void_p]),
     "bvc_sgd_step": (C.c_int, [C.c_void_p, C.c_int32, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int32,
                                C.c_void_p, C.c_void_p, C.c_void_p]),
+    "bvc_jepa_apply_masks": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32,
+                                       C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "bvc_jepa_apply_masks_bwd": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
+                                           C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "bvc_repeat_interleave_batch": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
+                                              C.c_void_p]),
+    "bvc_jepa_targets": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32,
+                                   C.c_int32, C.c_int32, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "bvc_smooth_l1_slots": (C.c_int64, [C.c_int64]),
+    "bvc_smooth_l1_fwd": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_float, C.c_void_p, C.c_void_p]),
+    "bvc_smooth_l1_bwd": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_float, C.c_void_p, C.c_void_p,
+                                    C.c_void_p]),
+    "bvc_ema_update": (C.c_int, [C.c_void_p, C.c_int32, C.c_double, C.c_void_p]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 
@@ -371,4 +384,66 @@ def nce_normalize_bwd(dfhat, feats, inv_norm, n, D, eps, dfeats):
     with _Timed("nce_rows", 0.0, float(n) * D * (feats.element_size() + 8)):
         _check(load().bvc_nce_normalize_bwd(_p(dfhat), _p(feats), is_bf16, feats.stride(0), _p(inv_norm), n, D, eps,
                                             _p(dfeats), _stream()), "bvc_nce_normalize_bwd")
+    _count()
+
+
+# ------------------------------------------------------------------------------------------------ JEPA pieces
+def jepa_apply_masks(x, idx, B, N, D, n_masks, K, repeat, out, status=None):
+    _cuda(x, idx, out)
+    nbytes = float(n_masks) * B * K * D * x.element_size() * (1 + repeat)
+    with _Timed("jepa_apply_masks", 0.0, nbytes):
+        _check(load().bvc_jepa_apply_masks(_p(x), x.element_size(), B, N, D, _p(idx), n_masks, K, repeat, _p(out),
+                                           _p(status), _stream()), "bvc_jepa_apply_masks")
+    _count()
+
+
+def jepa_apply_masks_bwd(dy, idx, B, N, D, n_masks, K, dx):
+    _cuda(dy, idx, dx)
+    with _Timed("jepa_apply_masks_bwd", 0.0, float(dx.numel() + 3 * dy.numel()) * dy.element_size()):
+        _check(load().bvc_jepa_apply_masks_bwd(_p(dy), dy.element_size(), B, N, D, _p(idx), n_masks, K, _p(dx),
+                                               _stream()), "bvc_jepa_apply_masks_bwd")
+    _count(n_masks)
+
+
+def repeat_interleave_batch(x, slab_bytes, B, n_groups, repeat, out):
+    _cuda(x, out)
+    with _Timed("repeat_interleave_batch", 0.0, float(n_groups) * B * slab_bytes * (1 + repeat)):
+        _check(load().bvc_repeat_interleave_batch(_p(x), slab_bytes, B, n_groups, repeat, _p(out), _stream()),
+               "bvc_repeat_interleave_batch")
+    _count()
+
+
+def jepa_targets(h, idx, B, N, D, n_masks, K, repeat, eps, out, status=None):
+    _cuda(h, idx, out)
+    nbytes = float(n_masks) * B * K * D * (h.element_size() + 4 * repeat)
+    with _Timed("jepa_targets", 0.0, nbytes):
+        _check(load().bvc_jepa_targets(_p(h), 1 if h.dtype == torch.float32 else 0, B, N, D, _p(idx), n_masks, K,
+                                       repeat, eps, _p(out), _p(status), _stream()), "bvc_jepa_targets")
+    _count()
+
+
+def smooth_l1_slots(n):
+    return int(load().bvc_smooth_l1_slots(n))
+
+
+def smooth_l1_fwd(z, h, n, beta, partials):
+    _cuda(z, h, partials)
+    with _Timed("smooth_l1_fwd", 0.0, float(n) * (z.element_size() + 4)):
+        _check(load().bvc_smooth_l1_fwd(_p(z), 1 if z.dtype == torch.float32 else 0, _p(h), n, beta, _p(partials),
+                                        _stream()), "bvc_smooth_l1_fwd")
+    _count()
+
+
+def smooth_l1_bwd(z, h, n, beta, grad_out, dz):
+    _cuda(z, h, grad_out, dz)
+    with _Timed("smooth_l1_bwd", 0.0, float(n) * (2 * z.element_size() + 4)):
+        _check(load().bvc_smooth_l1_bwd(_p(z), 1 if z.dtype == torch.float32 else 0, _p(h), n, beta, _p(grad_out),
+                                        _p(dz), _stream()), "bvc_smooth_l1_bwd")
+    _count()
+
+
+def ema_update(table, n_entries, momentum, total_elems):
+    _cuda(table)
+    with _Timed("ema_update", 0.0, float(total_elems) * 12):
+        _check(load().bvc_ema_update(_p(table), n_entries, float(momentum), _stream()), "bvc_ema_update")
     _count()

@@ -28,7 +28,7 @@ extern "C" {
 #define BVC_ERR_ARG (-1)
 #define BVC_ERR_DRIVER (-2)
 #define BVC_ERR_LAUNCH (-3)
-#define BVC_ABI_VERSION 10
+#define BVC_ABI_VERSION 11
 
 /* library / build info: returns BVC_ABI_VERSION (bumped when a signature changes) */
 int bvc_abi_version(void);
@@ -227,6 +227,43 @@ int bvc_nce_grad(const float* S, int64_t lds, const uint8_t* pos_mask, const uin
                  const float* out4, const float* grad_out, void* g_split, void* stream);
 int bvc_nce_normalize_bwd(const float* dfhat, const void* feats, int32_t feats_is_bf16, int64_t ld,
                           const float* inv_norm, int32_t n, int32_t D, float eps, float* dfeats, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * Predictive (JEPA) path, the pieces beside its ViT blocks.  idx = the list of masks
+ * stacked: int64 [n_masks, B, K] indices of kept patches in [0, N) (what MaskCollator / update_masks produce,
+ * pretraining/predictive/mask.py:21-38, :161-219).  An index outside [0, N) sets status[0] = 1 (if given) and yields a
+ * zero row (torch.gather raises; the host mirror raises when it checks the flag).
+ *   bvc_jepa_apply_masks     : mask.py:58-67 apply_masks -- out[(i*repeat + r)*B + b, k, :] = x[b, idx[i,b,k], :]
+ *                              (repeat = 1 is apply_masks itself; repeat > 1 also applies tensors.py:65-71
+ *                              repeat_interleave_batch(., B, repeat) to the result).  elem_bytes 2 / 4, D*elem_bytes % 16 == 0.
+ *   bvc_jepa_apply_masks_bwd : its autograd backward -- dx zero-filled, then dx[b, idx[i,b,k], :] += dy[i*B + b, k, :]
+ *                              mask after mask, LAST mask first (autograd's accumulation order; bit-exact, no atomics;
+ *                              requires the indices of ONE mask to be unique per sample, which block masks are)
+ *   bvc_repeat_interleave_batch : tensors.py:65-71 on x [n_groups*B, slab] -> out [n_groups*repeat*B, slab]
+ *   bvc_jepa_targets         : pretrain_jepa.py:384-392 in one pass -- F.layer_norm(h, (D,)) (eps, no affine, fp32
+ *                              statistics), apply_masks(., masks_pred), repeat_interleave_batch(., B, repeat):
+ *                              out fp32 [(n_masks*repeat*B), K, D].  Only the gathered rows are normalised.  D <= 1024.
+ *   bvc_smooth_l1_fwd / bwd  : F.smooth_l1_loss(z, h) (pretrain_jepa.py:399-402; mean reduction, beta) --
+ *                              fwd writes bvc_smooth_l1_slots(n) partial sums, bvc_loss_finalize(partials, slots, n, ...)
+ *                              makes the mean; bwd: dz = grad_out[0] * (|d| < beta ? d/beta : sign d) / n in z's dtype
+ *   bvc_ema_update           : pretrain_jepa.py:426-432 for every parameter in one launch; table = device array of
+ *                              { float* dst; const float* src; int64_t n; } (24 bytes each):
+ *                              dst = fl(fl(m*dst) + fl((1-m)*src)) with m, (1-m) rounded to fp32 as torch does
+ * ------------------------------------------------------------------------------------------------------ */
+int bvc_jepa_apply_masks(const void* x, int32_t elem_bytes, int32_t B, int32_t N, int32_t D, const int64_t* idx,
+                         int32_t n_masks, int32_t K, int32_t repeat, void* out, int32_t* status, void* stream);
+int bvc_jepa_apply_masks_bwd(const void* dy, int32_t elem_bytes, int32_t B, int32_t N, int32_t D, const int64_t* idx,
+                             int32_t n_masks, int32_t K, void* dx, void* stream);
+int bvc_repeat_interleave_batch(const void* x, int64_t slab_bytes, int32_t B, int32_t n_groups, int32_t repeat,
+                                void* out, void* stream);
+int bvc_jepa_targets(const void* h, int32_t h_is_f32, int32_t B, int32_t N, int32_t D, const int64_t* idx,
+                     int32_t n_masks, int32_t K, int32_t repeat, float eps, float* out, int32_t* status, void* stream);
+int64_t bvc_smooth_l1_slots(int64_t n);
+int bvc_smooth_l1_fwd(const void* z, int32_t z_is_f32, const float* h, int64_t n, float beta, float* partials,
+                      void* stream);
+int bvc_smooth_l1_bwd(const void* z, int32_t z_is_f32, const float* h, int64_t n, float beta, const float* grad_out,
+                      void* dz, void* stream);
+int bvc_ema_update(const void* table, int32_t n_entries, double momentum, void* stream);
 
 #ifdef __cplusplus
 }

@@ -63,3 +63,25 @@ def simclr_feats(g):
     feats[1::2] = 0.7 * feats[0::2] + 0.3 * feats[1::2]
     assert abs(float(feats.double().sum()) - float(g["feats_checksum"])) < 1e-6
     return feats
+
+
+def jepa_case(tag):
+    """Inputs of tests/golden/jepa_<tag>.npz regenerated in the generator's draw order (tools/make_golden_jepa.py):
+    returns (golden npz, h, masks_enc list, masks_pred list, z noise, gather-backward weights w, q list, k list)."""
+    import os
+    import numpy as np
+    import torch
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", f"jepa_{tag}.npz"))
+    B, D, N = int(g["B"]), int(g["D"]), int(g["N"])
+    rng = np.random.default_rng(int(g["seed"]))
+    h = torch.from_numpy(rng.standard_normal((B, N, D)).astype(np.float32) * 1.7 + 0.3)
+    m_enc = [torch.from_numpy(m) for m in g["masks_enc"]]
+    m_pred = [torch.from_numpy(m) for m in g["masks_pred"]]
+    K = m_pred[0].shape[1]
+    tshape = (len(m_pred) * len(m_enc) * B, K, D)
+    noise = torch.from_numpy(rng.standard_normal(tshape).astype(np.float32)) * 0.8
+    w = torch.from_numpy(rng.standard_normal((len(m_pred) * B, K, D)).astype(np.float32))
+    shapes = ((D, 7), (13,), (5, D))
+    q = [torch.from_numpy(rng.standard_normal(s).astype(np.float32)) for s in shapes]
+    k = [torch.from_numpy(rng.standard_normal(s).astype(np.float32)) for s in shapes]
+    return g, h, m_enc, m_pred, noise, w, q, k

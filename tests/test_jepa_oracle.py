@@ -1,0 +1,45 @@
+"""CPU: the JEPA oracle (oracle/jepa_oracle.py) against fixtures made by the reference's own functions
+(tools/make_golden_jepa.py: predictive/mask.py MaskCollator, update_masks, apply_masks; tensors.py
+repeat_interleave_batch; pretrain_jepa.py:384-402, :426-432)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import jepa_oracle as J
+from tests.helpers import jepa_case
+
+
+@pytest.mark.parametrize("tag", ["tiny", "vitb"])
+def test_jepa_oracle_matches_reference_fixtures(tag):
+    g, h, m_enc, m_pred, noise, w, q, k = jepa_case(tag)
+    B = h.shape[0]
+    t = J.jepa_targets(h, m_pred, len(m_enc))
+    ctx = J.apply_masks(h, m_enc)
+    assert torch.equal(ctx[:, :2, :8], torch.from_numpy(g["ctx_head"]))          # index work: bit-exact
+    assert float(ctx.double().sum()) == float(g["ctx_checksum"])
+    np.testing.assert_allclose(t[:, :2, :8].numpy(), g["targets_head"], rtol=0, atol=2e-6)
+    np.testing.assert_allclose(float(t.double().abs().sum()), float(g["targets_abs_checksum"]), rtol=1e-6)
+    if "targets" in g:
+        np.testing.assert_allclose(t.numpy(), g["targets"], rtol=0, atol=2e-6)
+        assert torch.equal(ctx, torch.from_numpy(g["ctx"]))
+    # smooth-L1 and its gradient (upstream gradient 3.0 as in the generator)
+    t_ref = torch.from_numpy(g["targets"]) if "targets" in g else t
+    z = (t_ref + noise).requires_grad_(True)
+    loss = J.smooth_l1_loss(z, t_ref)
+    (loss * 3.0).backward()
+    np.testing.assert_allclose(float(loss), float(g["loss"]), rtol=2e-6)
+    np.testing.assert_allclose(z.grad[:, :2, :8].numpy(), g["dz_head"], rtol=1e-5, atol=1e-9)
+    # gather backward: rows hit by several prediction blocks accumulate
+    hx = h.clone().requires_grad_(True)
+    (J.apply_masks(hx, m_pred) * w).sum().backward()
+    np.testing.assert_allclose(hx.grad[:, 1372:1380, :8].numpy(), g["dh_rows"], rtol=0, atol=1e-6)
+    np.testing.assert_allclose(float(hx.grad.double().abs().sum()), float(g["dh_checksum"]), rtol=1e-6)
+    # repeat_interleave_batch: block order
+    x = torch.arange(3 * B * 2, dtype=torch.float32).reshape(3 * B, 2)
+    r = J.repeat_interleave_batch(x, B, 2)
+    assert r.shape[0] == 6 * B and torch.equal(r[:B], x[:B]) and torch.equal(r[B:2 * B], x[:B])
+    assert torch.equal(r[2 * B:3 * B], x[B:2 * B])
+    # momentum update: bit-exact (three fp32 roundings)
+    new = J.ema_update(q, k, float(g["momentum"]))
+    for i, kn in enumerate(new):
+        assert torch.equal(kn, torch.from_numpy(g[f"ema_k{i}"]))

@@ -50,6 +50,20 @@ __device__ __forceinline__ uint4 ldv_u4(const void* p) {
   return v;
 }
 
+// Explicit shared-memory accesses by 32-bit shared address.  Staging buffers carved out of the dynamic shared-memory
+// block by integer arithmetic are GENERIC pointers to the compiler: it emits LD.E / ST.E (generic path, long
+// scoreboard) and, unable to rule out aliasing with the global stores of a fused epilogue, serialises every staging
+// load behind the previous row's stores (ncu source view of the GELU GEMM: 8 dependent generic-load round trips per
+// 32-column chunk, 14 % of all stall samples).  These keep the accesses on LDS / STS and in program order.
+__device__ __forceinline__ float4 lds_f4(uint32_t saddr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+  return v;
+}
+__device__ __forceinline__ void sts_u4(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d));
+}
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&t);

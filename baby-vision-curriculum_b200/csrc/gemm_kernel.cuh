@@ -326,7 +326,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     const int q = warp & 3;          // TMEM lane quadrant this warp may read
     const int half = e >> 2;         // which half of the BN columns
     constexpr int kColsPerWarp = BN / 2;
-    uint8_t* stg = staging + e * 4096;
+    const uint32_t stg_s = smem_u32(staging + e * 4096);  // explicit LDS / STS (see lds_f4 in bvc_ptx.cuh)
     const int c4 = lane & 7;         // phase 2: this lane's 4-column group inside the 32-column chunk
     const int rsub = lane >> 3;      // phase 2: row within each group of 4 rows
     const float alpha = p.alpha * (p.alpha_dev ? __ldg(p.alpha_dev) : 1.0f);
@@ -381,6 +381,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         }
       };
       if (kFast && interior && (EPI == EPI_RES || EPI == EPI_DGELU)) prefetch_chunk(0);
+      // the bias of the chunk after the current one is always in flight (volatile: ptxas otherwise sinks the load next
+      // to its use, and its L2 latency was exposed once per 32-column chunk: 5 % of the GELU GEMM's stall samples)
+      float4 bias_nxt = make_float4(0.f, 0.f, 0.f, 0.f);
+      auto bias_chunk = [&](int cc_n) {
+        const int col_n = n0 + half * kColsPerWarp + cc_n + c4 * 4;
+        if (p.bias && col_n < p.N) bias_nxt = ldv_f4(p.bias + col_n);
+      };
+      bias_chunk(0);
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       float lsum = 0.f;
@@ -400,22 +408,25 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         }
 #pragma unroll
         for (int c = 0; c < 8; ++c)
-          *reinterpret_cast<uint4*>(stg + lane * 128 + ((c ^ (lane & 7)) << 4)) =
-              make_uint4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+          sts_u4(stg_s + lane * 128 + ((c ^ (lane & 7)) << 4), v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
         __syncwarp();
         const int col = n0 + c_tile + c4 * 4;
+        const float4 bias_cur = bias_nxt;
+        if (cc + 32 < kColsPerWarp) bias_chunk(cc + 32);
+        // this lane's 8 rows of the transposed chunk, all requested before any of the row loop's global stores
+        float4 tv[8];
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int rl = it * 4 + rsub;
+          tv[it] = lds_f4(stg_s + rl * 128 + ((c4 ^ (rl & 7)) << 4));
+        }
         if (kFast && interior) {
           // ---------------------------------------------------------------- interior tile, non-generic variant:
           // no row / column guards, no segment remap, pointers advance by a constant stride, math on fp32x2 pairs.
           // (The guarded path below costs ~30 instructions per output element on the GELU variant -- ncu: FFMA 8,
           // IMAD/IADD3/ISETP/BRA 9 -- which made the K = 384 decoder GEMMs epilogue-bound.)
           const long long r0 = rbase + rsub;
-          uint64_t b01 = 0, b23 = 0;
-          if (p.bias) {
-            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
-            b01 = pack2(b4.x, b4.y);
-            b23 = pack2(b4.z, b4.w);
-          }
+          const uint64_t b01 = pack2(bias_cur.x, bias_cur.y), b23 = pack2(bias_cur.z, bias_cur.w);  // zeros without bias
           const uint64_t al2 = pack2(alpha, alpha);
           float4 pre_f[8];
           uint2 pre_h[8];
@@ -434,8 +445,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
           uint64_t cs01 = 0, cs23 = 0;  // (0.f, 0.f): this lane's column sums over its 8 rows
 #pragma unroll
           for (int it = 0; it < 8; ++it) {
-            const int rl = it * 4 + rsub;
-            const float4 t = *reinterpret_cast<const float4*>(stg + rl * 128 + ((c4 ^ (rl & 7)) << 4));
+            const float4 t = tv[it];
             uint64_t v01 = pack2(t.x, t.y), v23 = pack2(t.z, t.w);
             if (has_alpha) {
               v01 = fmul2(v01, al2);
@@ -500,8 +510,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
           continue;
         }
         if (col < p.N) {
-          float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (p.bias) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+          const float4 bias4 = bias_cur;
           // global operands of the fused epilogue first, all 8 rows in flight at once (issuing them inside the
           // row loop serialises one DRAM round trip per row: measured 5x slower on the residual / GELU' GEMMs)
           float4 pre_f[8];
@@ -556,7 +565,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             const int rl = it * 4 + rsub;
             const int r = rbase + rl;
             if (r >= p.M) continue;
-            const float4 t = *reinterpret_cast<const float4*>(stg + rl * 128 + ((c4 ^ (rl & 7)) << 4));
+            const float4 t = tv[it];
             float x[4] = {t.x * alpha, t.y * alpha, t.z * alpha, t.w * alpha};
             long long R = r;
             if (kSeg && p.out_seg > 0)

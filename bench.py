@@ -18,6 +18,8 @@ cpu_baseline : the reference's own CPU path (HF transformers VideoMAEForPreTrain
                bounded sample.   --impl reference prints that as its own line.
 """
 import argparse
+import contextlib
+import io
 import json
 import os
 import statistics
@@ -462,7 +464,19 @@ if __name__ == "__main__":
                     help="fused: bvc.FusedSGD (libbvc.so bvc_sgd_step); torch: torch.optim.SGD as in the reference")
     ap.add_argument("--detail", default="", help="write a per-shape kernel time breakdown (JSON) to this path")
     a = ap.parse_args()
-    if a.impl == "reference":
-        run_reference(a)
-    else:
-        run_ours(a)
+    # stdout carries exactly ONE line, the JSON result: everything else a library writes to file descriptor 1 while the
+    # benchmark runs (NCCL prints its version banner there when NCCL_DEBUG is set in the environment) goes to stderr
+    sys.stdout.flush()
+    _json_fd = os.dup(1)
+    os.dup2(2, 1)
+    _buf = io.StringIO()
+    with contextlib.redirect_stdout(_buf):
+        if a.impl == "reference":
+            run_reference(a)
+        else:
+            run_ours(a)
+    _lines = [ln for ln in _buf.getvalue().splitlines() if ln.strip()]
+    for ln in _lines[:-1]:
+        sys.stderr.write(ln + "\n")
+    if _lines:
+        os.write(_json_fd, (_lines[-1] + "\n").encode())

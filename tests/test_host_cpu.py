@@ -141,3 +141,28 @@ def test_simclr_host_side(golden_dir):
         bvc.info_nce_loss(0.1, (pos, neg), torch.zeros(16, 32))
     with pytest.raises(ValueError):
         bvc.info_nce_loss(0.1, (pos, neg), torch.zeros(16))
+
+
+def test_jepa_host_mirror_validates_before_touching_cuda():
+    """bvc_b200.apply_masks / repeat_interleave_batch / smooth_l1_loss / ema_update (jepa.py): argument errors are Python
+    ValueErrors like the reference's torch calls would raise; CPU tensors never reach a kernel (BvcError, no fallback)."""
+    import pytest
+    import torch
+    import bvc_b200 as bvc
+    x = torch.randn(2, 10, 8)
+    with pytest.raises(ValueError):
+        bvc.apply_masks(x, [])
+    with pytest.raises(ValueError):
+        bvc.apply_masks(x, [torch.zeros(2, 3, dtype=torch.int64), torch.zeros(2, 4, dtype=torch.int64)])
+    with pytest.raises(ValueError):
+        bvc.apply_masks(torch.randn(10, 8), [torch.zeros(2, 3, dtype=torch.int64)])
+    with pytest.raises(ValueError):
+        bvc.repeat_interleave_batch(torch.randn(5, 8), 2, 2)
+    with pytest.raises(ValueError):
+        bvc.smooth_l1_loss(torch.randn(4, 4), torch.randn(4, 5))
+    with pytest.raises(ValueError):
+        bvc.ema_update([torch.randn(3)], [], 0.99)
+    with pytest.raises(ValueError):
+        bvc.jepa_targets(torch.randn(2, 10, 6), [torch.zeros(2, 3, dtype=torch.int64)], 1)   # D % 4 != 0
+    with pytest.raises(bvc.BvcError):
+        bvc.apply_masks(x, [torch.zeros(2, 3, dtype=torch.int64)])

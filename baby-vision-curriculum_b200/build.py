@@ -15,7 +15,7 @@ CSRC = os.path.join(HERE, "csrc")
 ROOT = os.path.dirname(HERE)
 LIB = os.path.join(HERE, "libbvc.so")
 OBJ_DIR = os.path.join(HERE, "build")
-SOURCES = ["gemm.cu", "gemm_bn64.cu", "gemm_bn128.cu", "gemm_bn192.cu", "gemm_bn256.cu", "gemm_pair128.cu", "gemm_pair192.cu", "gemm_pair256.cu", "rows.cu", "patchify.cu", "attn.cu", "optim.cu", "nce.cu", "jepa.cu"]
+SOURCES = ["gemm.cu", "gemm_bn64.cu", "gemm_bn128.cu", "gemm_bn192.cu", "gemm_bn256.cu", "gemm_pair128.cu", "gemm_pair192.cu", "gemm_pair256.cu", "rows.cu", "patchify.cu", "attn.cu", "attn_small.cu", "optim.cu", "nce.cu", "jepa.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--use_fast_math",
          "-Xcompiler", "-fPIC", "-Xptxas", "-v"]

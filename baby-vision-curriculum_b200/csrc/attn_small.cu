@@ -1,0 +1,304 @@
+// attn_small.cu -- attention forward for SHORT sequences (S <= 192: the ViT encoder's 160 visible tokens at mask ratio
+// 0.9), head_dim 64.  Same contract as attn_fwd_kernel (attn.cu); bvc_attn_fwd dispatches here.
+//
+// Why a second kernel: at S = 160 the general kernel walks two ragged 128-wide K/V tiles per query tile (39 % of the
+// score math is useful) through a pipeline that is refilled every two tiles.  Here the WHOLE sequence of one (clip,
+// head) is resident: K and V are two contiguous [128][64] tiles, so ONE tcgen05.mma with N = S16 = roundup16(S) gives a
+// query tile's full score row (the 128B-swizzled 8-row groups of the second tile continue the first tile's), the
+// softmax is a plain two-pass row softmax (no running maximum, no rescale), P goes back into the TMEM columns its
+// scores came from (packed bf16, chunk c of P lands on columns of score chunks <= c, which are already in registers)
+// and feeds O = P V as an A-from-TMEM operand with S16 / 16 k-steps.
+//
+// Persistent, one CTA per SM over (clip, head) items, shared memory double-buffered across items:
+//   warp 0 TMA loads (Q0, Q1, K0|K1, V0|V1 of item k + 1 while item k computes), warp 1 MMA issue, warp 2 TMA stores,
+//   warps 4-7 / 8-11 softmax + epilogue of query tile 0 / 1 (thread = one query row).
+// TMEM (512 columns): S0 / P0 at 0, S1 / P1 at 192, O0 at 384, O1 at 448.
+#include "attn_common.cuh"
+
+namespace bvc {
+
+constexpr int kSmallMaxS = 192;
+constexpr int kSmThreads = 384;
+constexpr int kSmItemBytes = 6 * kTileBytes;               // Q0 Q1 | K0 K1 | V0 V1
+constexpr int kSmSmem = 2 * kSmItemBytes + 256;
+
+__global__ void __launch_bounds__(kSmThreads, 1)
+attn_small_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_out,
+                      float* __restrict__ lse, int S, int H, int n_work, float scale_log2) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * kSmItemBytes);
+  uint64_t* in_full = bars + 0;    // [2] TMA -> MMA: the item's six tiles landed
+  uint64_t* in_empty = bars + 2;   // [2] store warp -> TMA: the item's buffer (Q tiles doubled as O staging) is free
+  uint64_t* s_full = bars + 4;     // [2 query tiles] MMA -> softmax group
+  uint64_t* p_full = bars + 6;     // [2] softmax group -> MMA: P is in TMEM
+  uint64_t* o_full = bars + 8;     // [2] MMA -> softmax group: O = P V complete
+  uint64_t* o_free = bars + 10;    // [2] softmax group -> MMA: O (and with it S / P) of the item has been read
+  uint64_t* epi_full = bars + 12;  // softmax groups -> store warp: O tiles staged
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int S16 = (S + 15) & ~15;
+  const int n_q = S > kTile ? 2 : 1;  // query tiles (= softmax groups at work)
+  const int n_my = (n_work - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  auto item_bh = [&](int k) { return (int)blockIdx.x + k * (int)gridDim.x; };
+
+  if (threadIdx.x == 0) {
+    if ((smem_u32(smem) & 1023u) != 0) __trap();
+    tma_prefetch_desc(&tm_qkv);
+    tma_prefetch_desc(&tm_out);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&in_full[i], 1);
+      mbar_init(&in_empty[i], 1);
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 4);
+      mbar_init(&o_full[i], 1);
+      mbar_init(&o_free[i], 4);
+    }
+    mbar_init(epi_full, 4 * n_q);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int k = 0; k < n_my; ++k) {
+        const int bh = item_bh(k), h = bh % H, b = bh / H, buf = k & 1;
+        uint8_t* base = smem + buf * kSmItemBytes;
+        mbar_wait(&in_empty[buf], ((uint32_t)(k >> 1) & 1u) ^ 1u);
+        mbar_expect_tx(&in_full[buf], (n_q == 2 ? 6 : 3) * kTileBytes);
+        tma_load_4d(base, &tm_qkv, &in_full[buf], 0, h, 0, b);
+        tma_load_4d(base + 2 * kTileBytes, &tm_qkv, &in_full[buf], 0, H + h, 0, b);
+        tma_load_4d(base + 4 * kTileBytes, &tm_qkv, &in_full[buf], 0, 2 * H + h, 0, b);
+        if (n_q == 2) {  // rows 128 .. 255: zero-filled past S
+          tma_load_4d(base + kTileBytes, &tm_qkv, &in_full[buf], 0, h, kTile, b);
+          tma_load_4d(base + 3 * kTileBytes, &tm_qkv, &in_full[buf], 0, H + h, kTile, b);
+          tma_load_4d(base + 5 * kTileBytes, &tm_qkv, &in_full[buf], 0, 2 * H + h, kTile, b);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // MMA issuer: warp-uniform control flow, one elected lane issues (see elect_one in bvc_ptx.cuh)
+    const uint32_t idesc_s = umma_idesc_bf16(S16, 0, 0, 128);
+    constexpr uint32_t idesc_o = umma_idesc_bf16(64, 0, 1, 128);
+    const int ksteps = S16 >> 4;
+    for (int k = 0; k < n_my; ++k) {
+      const int buf = k & 1;
+      const uint32_t base = smem_u32(smem + buf * kSmItemBytes);
+      mbar_wait(&in_full[buf], (uint32_t)(k >> 1) & 1u);
+      for (int t = 0; t < n_q; ++t) {
+        // S_t overwrites the previous item's S / P columns: its P V must be complete (the O columns are separate, so
+        // the scores of item k are computed while the group still drains O of item k - 1)
+        if (k > 0) mbar_wait(&o_full[t], (uint32_t)(k - 1) & 1u);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint64_t dQ = desc_k(base + t * kTileBytes, 0), dK = desc_k(base + 2 * kTileBytes, 0);
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            umma_bf16_ss(tmem_base + (uint32_t)t * 192, dQ + 2 * kk, dK + 2 * kk, idesc_s, kk > 0);
+          umma_commit(&s_full[t]);
+        }
+        __syncwarp();
+      }
+      for (int t = 0; t < n_q; ++t) {
+        mbar_wait(&p_full[t], (uint32_t)k & 1u);
+        if (k > 0) mbar_wait(&o_free[t], (uint32_t)(k - 1) & 1u);  // P V overwrites O_t: the group has read item k - 1's
+        tc_fence_after();
+        if (elect_one()) {
+          // O_t = P_t V: A = P (TMEM, packed bf16, 8 columns per K = 16 step), B = V (MN-major: n = d, k = key; the
+          // second V tile continues the first one's 16-row k-steps)
+          const uint64_t dV = desc_mn(base + 4 * kTileBytes, 0, 8192);
+          const uint32_t aP = tmem_base + (uint32_t)t * 192, dO = tmem_base + 384 + (uint32_t)t * 64;
+          for (int kk = 0; kk < ksteps; ++kk) umma_bf16_ts(dO, aP + kk * 8, dV + 128 * kk, idesc_o, kk > 0);
+          umma_commit(&o_full[t]);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 2) {
+    for (int k = 0; k < n_my; ++k) {
+      const int bh = item_bh(k), h = bh % H, b = bh / H, buf = k & 1;
+      uint8_t* base = smem + buf * kSmItemBytes;
+      mbar_wait(epi_full, (uint32_t)k & 1u);
+      if (lane == 0) {
+        tma_store_4d(&tm_out, base, 0, h, 0, b);  // the store clips the rows past the end of the sequence
+        if (n_q == 2) tma_store_4d(&tm_out, base + kTileBytes, 0, h, kTile, b);
+        tma_store_commit();
+        tma_store_wait_read0();
+        mbar_arrive(&in_empty[buf]);
+      }
+      __syncwarp();
+    }
+    if (lane == 0) tma_store_wait0();
+  } else if (warp >= 4) {
+    const int q4 = warp & 3;
+    const int t = (warp - 4) >> 2;
+    if (t < n_q) {
+      const int row = q4 * 32 + lane;
+      const uint32_t lane_base = (uint32_t)(q4 * 32) << 16;
+      const uint32_t mS = tmem_base + (uint32_t)t * 192 + lane_base, mO = tmem_base + 384 + (uint32_t)t * 64 + lane_base;
+      const uint64_t c2 = pack2(scale_log2, scale_log2);
+      const int n32 = S16 >> 5;          // full 32-column chunks of the score row
+      const bool tail16 = (S16 & 16) != 0;  // plus one 16-column chunk
+      // a warp whose 32 rows all lie past the end of the sequence (S = 160: three of the second tile's four warps)
+      // only keeps the barrier protocol alive: its rows of P / O are garbage that no valid row depends on and that the
+      // TMA store clips, and it no longer competes for the MUFU pipe with the warps that have work
+      const bool live = t * kTile + q4 * 32 < S;
+      for (int k = 0; k < n_my; ++k) {
+        const int bh = item_bh(k), buf = k & 1;
+        mbar_wait(&s_full[t], (uint32_t)k & 1u);
+        if (!live) {
+          if (lane == 0) mbar_arrive(&p_full[t]);
+          mbar_wait(&o_full[t], (uint32_t)k & 1u);
+          if (lane == 0) {
+            mbar_arrive(&o_free[t]);
+            mbar_arrive(epi_full);
+          }
+          continue;
+        }
+        tc_fence_after();
+        // pass 1: row maximum of the raw scores (columns >= S are padding: K rows zero-filled by TMA)
+        float mx = -INFINITY;
+        for (int c = 0; c < n32; ++c) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(mS + c * 32, v);
+          tmem_ld_wait();
+          if (c * 32 + 32 <= S) {
+            float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+            for (int i = 0; i < 32; ++i) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(v[i]));
+            mx = fmaxf(mx, fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])));
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (c * 32 + i < S) mx = fmaxf(mx, __uint_as_float(v[i]));
+          }
+        }
+        if (tail16) {
+          uint32_t v[16];
+          tmem_ld_32x32b_x16(mS + n32 * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            if (n32 * 32 + i < S) mx = fmaxf(mx, __uint_as_float(v[i]));
+        }
+        const float m = mx * scale_log2;  // log2 domain (scale_log2 > 0)
+        const uint64_t m2 = pack2(-m, -m);
+        // pass 2: P = exp2(S * scale_log2 - m), row sum, packed bf16 P over the score columns already consumed
+        float l = 0.f;
+        uint64_t l2 = pack2(0.f, 0.f);
+        for (int c = 0; c < n32; ++c) {
+          uint32_t v[32], pk[16];
+          tmem_ld_32x32b_x32(mS + c * 32, v);
+          tmem_ld_wait();
+          if (c * 32 + 32 <= S) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              const uint64_t e2 = exp2_mufu2(ffma2(pack2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])), c2, m2));
+              float p0, p1;
+              unpack2(e2, p0, p1);
+              l2 = fadd2(l2, e2);
+              pk[i >> 1] = pack_bf16x2(p0, p1);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              float p0, p1;
+              unpack2(exp2_mufu2(ffma2(pack2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])), c2, m2)), p0, p1);
+              if (c * 32 + i >= S) p0 = 0.f;
+              if (c * 32 + i + 1 >= S) p1 = 0.f;
+              l += p0 + p1;
+              pk[i >> 1] = pack_bf16x2(p0, p1);
+            }
+          }
+          tmem_st_32x32b_x16(mS + c * 16, pk);
+        }
+        {
+          float la, lb;
+          unpack2(l2, la, lb);
+          l += la + lb;
+        }
+        if (tail16) {
+          uint32_t v[16], pk[8];
+          tmem_ld_32x32b_x16(mS + n32 * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; i += 2) {
+            float p0, p1;
+            unpack2(exp2_mufu2(ffma2(pack2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])), c2, m2)), p0, p1);
+            if (n32 * 32 + i >= S) p0 = 0.f;
+            if (n32 * 32 + i + 1 >= S) p1 = 0.f;
+            l += p0 + p1;
+            pk[i >> 1] = pack_bf16x2(p0, p1);
+          }
+          tmem_st_32x32b_x8(mS + n32 * 16, pk);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[t]);
+        // epilogue: O / l -> bf16 -> the item's Q tile (no MMA reads it any more), 128B-swizzled -> TMA store
+        mbar_wait(&o_full[t], (uint32_t)k & 1u);
+        tc_fence_after();
+        const float inv_l = 1.0f / l;
+        uint8_t* stage = smem + buf * kSmItemBytes + t * kTileBytes;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint32_t ov[32];
+          tmem_ld_32x32b_x32(mO + c * 32, ov);
+          tmem_ld_wait();
+#pragma unroll
+          for (int gq = 0; gq < 4; ++gq) {
+            uint4 o4;
+            o4.x = pack_bf16x2(__uint_as_float(ov[gq * 8 + 0]) * inv_l, __uint_as_float(ov[gq * 8 + 1]) * inv_l);
+            o4.y = pack_bf16x2(__uint_as_float(ov[gq * 8 + 2]) * inv_l, __uint_as_float(ov[gq * 8 + 3]) * inv_l);
+            o4.z = pack_bf16x2(__uint_as_float(ov[gq * 8 + 4]) * inv_l, __uint_as_float(ov[gq * 8 + 5]) * inv_l);
+            o4.w = pack_bf16x2(__uint_as_float(ov[gq * 8 + 6]) * inv_l, __uint_as_float(ov[gq * 8 + 7]) * inv_l);
+            *reinterpret_cast<uint4*>(stage + row * 128 + (((c * 4 + gq) ^ (row & 7)) << 4)) = o4;
+          }
+        }
+        const int qrow = t * kTile + row;
+        if (qrow < S) lse[(long long)bh * S + qrow] = (m + log2f(l)) * 0.6931471805599453f;
+        tc_fence_before();
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&o_free[t]);
+          mbar_arrive(epi_full);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+int attn_small_fwd_launch(const void* qkv, int B, int S, int H, float scale, void* out, float* lse, cudaStream_t st) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    if (cudaFuncSetAttribute(attn_small_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmSmem) != cudaSuccess)
+      return BVC_ERR_LAUNCH;
+    attr_done = true;
+  }
+  CUtensorMap tm, to;
+  int rc = make_head_tmap(&tm, qkv, 3 * H, S, B);
+  if (rc) return rc;
+  rc = make_head_tmap(&to, out, H, S, B);
+  if (rc) return rc;
+  const long long n_work = (long long)B * H;
+  BVC_CHECK_ARG(n_work < (1ll << 30) && S <= kSmallMaxS);
+  const int grid = (int)(n_work < num_sms() ? n_work : num_sms());
+  attn_small_fwd_kernel<<<grid, kSmThreads, kSmSmem, st>>>(tm, to, lse, S, H, (int)n_work, scale * kLog2e);
+  BVC_CHECK_LAUNCH();
+  return BVC_OK;
+}
+
+}  // namespace bvc

@@ -354,6 +354,12 @@ def run_attn():
     attn_case(1, 1568, 2)
     attn_case(3, 200, 3)
     attn_case(2, 392, 6)
+    # short sequences: the whole-sequence-resident kernels of attn_small.cu (S <= 192), many items per CTA
+    attn_case(3, 192, 2)
+    attn_case(2, 144, 3)
+    attn_case(2, 100, 1)
+    attn_case(2, 129, 2)
+    attn_case(40, 160, 12)
 
 
 # ------------------------------------------------------------------------------------------------ perf probes

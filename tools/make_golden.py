@@ -110,8 +110,9 @@ def summarised_step(name, batch, fname):
         np.random.seed(0)
         mask = O.batch_tube_masks(batch, cfg.grid, 0.9)
         loss, logits, grads = run_hf(cfg, params, x, mask)
-        bloss, _, bgrads = run_hf(cfg, params, x, mask, bf16=True)
+        bloss, blogits, bgrads = run_hf(cfg, params, x, mask, bf16=True)
         flat = logits.flatten()
+        bsamp, fsamp = blogits.flatten()[::100003][:64].double(), flat[::100003][:64].double()
         bf16_dev = {k: abs(float(bgrads[k].double().norm()) - float(g.double().norm())) / max(float(g.double().norm()), 1e-30)
                     for k, g in grads.items()}
         bg = float(torch.sqrt(sum(g.double().pow(2).sum() for g in bgrads.values())))
@@ -119,6 +120,7 @@ def summarised_step(name, batch, fname):
         out[tag] = {
             # how far the reference's OWN bf16-autocast path is from its fp32 path on these inputs
             "hf_bf16_loss_rel": abs(float(bloss) - float(loss)) / float(loss),
+            "hf_bf16_logits_sample_rel_l2": float((bsamp - fsamp).norm() / fsamp.norm()),
             "hf_bf16_grad_norm_rel": bf16_dev,
             "hf_bf16_grad_global_norm_rel": abs(bg - fg) / fg,
             "hf_bf16_grad_global_rel_l2": float(torch.sqrt(sum((bgrads[k].double() - g.double()).pow(2).sum()
@@ -173,3 +175,5 @@ if __name__ == "__main__":
     summarised_step("small", 2, "small_step.json")
     if "--base" in sys.argv:
         summarised_step("base", 2, "base_step.json")
+    if "--large" in sys.argv:   # BASELINE.json configs[4]'s model (ViT-L/16), one clip
+        summarised_step("large", 1, "large_step.json")

@@ -1,8 +1,10 @@
 """Kernel-level parity of every libbvc.so entry point against fp64 torch references on the same seeded inputs
-(tools/gpu_selftest.py holds the cases: GEMM in all four operand-major combinations, every fused epilogue incl. split-K,
+(tools/gpu_selftest.py holds the cases: GEMM in all four operand-major combinations, on one-CTA tiles and on CTA pairs
+(tcgen05 cta_group::2, group "gemmpair"), every fused epilogue incl. split-K,
 GELU / GELU' / residual / row-gather / segment scatter / fused MSE / fused column sums, LayerNorm forward / backward with
 segment remaps, column sums, casts, decoder mask rows, tube-mask indexing + patchify + normalised-pixel target
-(bit-exact indices and visible-patch rows), attention forward / backward at S = 8 ... 1568 incl. ragged tiles).
+(bit-exact indices and visible-patch rows), attention forward / backward at S = 8 ... 1568 incl. ragged tiles and the
+short-sequence kernel of attn_small.cu).
 Each group runs in its own process so that a device trap in one group cannot poison the others; a group passes when
 every case printed PASS.  The end-to-end step parity lives in test_model_gpu.py."""
 import os
@@ -15,7 +17,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("group", ["rows", "patchify", "gemm00", "gemm01", "gemm10", "gemm11", "gemmx", "attn"])
+@pytest.mark.parametrize("group", ["rows", "patchify", "gemm00", "gemm01", "gemm10", "gemm11", "gemmx", "gemmpair", "attn"])
 def test_kernel_group(group):
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "gpu_selftest.py"), group], capture_output=True,
                        text=True, timeout=600)

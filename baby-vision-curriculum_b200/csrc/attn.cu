@@ -867,6 +867,8 @@ using namespace bvc;
 
 namespace bvc {
 int attn_small_fwd_launch(const void* qkv, int B, int S, int H, float scale, void* out, float* lse, cudaStream_t st);
+int attn_small_bwd_launch(const void* qkv, const void* dout, const float* lse, const float* delta, int B, int S, int H,
+                          float scale, void* dqkv, cudaStream_t st);
 // BVC_ATTN_SMALL=0 forces the general kernels for short sequences too (A/B measurements)
 static bool small_path_enabled() {
   static const bool on = []() {
@@ -920,6 +922,12 @@ extern "C" int bvc_attn_bwd(const void* qkv, const void* out, const void* dout, 
   if (g > (long long)num_sms() * 8) g = (long long)num_sms() * 8;
   attn_delta_kernel<<<(int)g, 256, 0, st>>>((const bf16*)out, (const bf16*)dout, delta, rows, S, H);
   BVC_CHECK_LAUNCH();
+  // short sequences: single-pass, whole-sequence-resident kernel (attn_small.cu); BVC_ATTN_SMALL_BWD=0 switches it off
+  static const bool small_bwd = []() {
+    const char* e = getenv("BVC_ATTN_SMALL_BWD");
+    return !(e && e[0] == '0');
+  }();
+  if (S <= 160 && small_path_enabled() && small_bwd) return attn_small_bwd_launch(qkv, dout, lse, delta, B, S, H, scale, dqkv, st);
   CUtensorMap tq, td;
   int rc = make_head_tmap(&tq, qkv, 3 * H, S, B);
   if (rc) return rc;

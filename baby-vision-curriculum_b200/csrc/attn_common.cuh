@@ -43,6 +43,12 @@ __device__ __forceinline__ void tmem_st_32x32b_x8(uint32_t taddr, const uint32_t
                "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
                : "memory");
 }
+__device__ __forceinline__ void tmem_ld_32x32b_x8(uint32_t taddr, uint32_t (&v)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr)
+               : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // K-major operand tile [rows][64]: k-step (16 elements) = +32 bytes inside the swizzle atom
@@ -59,10 +65,10 @@ __device__ __forceinline__ uint32_t ptile_chunk_off(int row, int chunk16 /*0..15
 
 
 // [B, S, heads_total, 64] bf16 viewed as a 4-D tensor; box = 64 x 1 x 128 x 1 -> one [128 rows][64] tile
-static inline int make_head_tmap(CUtensorMap* tm, const void* base, int heads_total, int S, int B) {
+static inline int make_head_tmap(CUtensorMap* tm, const void* base, int heads_total, int S, int B, int box_rows = 128) {
   const uint64_t dims[4] = {64, (uint64_t)heads_total, (uint64_t)S, (uint64_t)B};
   const uint64_t strides[3] = {128, (uint64_t)heads_total * 128, (uint64_t)S * heads_total * 128};
-  const uint32_t box[4] = {64, 1, 128, 1};
+  const uint32_t box[4] = {64, 1, (uint32_t)box_rows, 1};
   return make_tmap(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 

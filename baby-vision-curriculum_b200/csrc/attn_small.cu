@@ -281,6 +281,295 @@ attn_small_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_c
   }
 }
 
+// ================================================================================================ backward, S <= 160
+// ONE pass per (clip, head) with everything resident (the general kernels need two passes, each recomputing the
+// scores, and walk two ragged 128-tiles per dimension at S = 160: 7 MMAs and 2 exponentials per score where 5 and 1
+// suffice, plus a pipeline refill every two tiles).  Rows = queries:
+//   per query tile t:  S_t = Q_t K^T, dP_t = dO_t V^T (N = S16)  ->  P = exp2(S c - lse), dS = P (dP - delta) scale
+//                      written as bf16 to shared memory in [query row][key] order, one 64-key atom after the other;
+//                      dQ_t = dS_t K reads it K-major (A operand, M = queries),
+//   once per item:     dV = P^T dO and dK = dS^T Q read THE SAME tiles MN-major (A operand, M = keys, K = queries):
+//                      the UMMA descriptor's major bit transposes P / dS for free, nothing is stored twice.
+// TMEM: S [0,160), dP [160,320), dQ_0 [320,384), dQ_1 [384,448); when the last tile's scores have been read, dV_0, dV_1,
+// dK_0, dK_1 take [0,256).  The six output tiles leave through the (then dead) P / dS buffers and TMA stores, which clip
+// the rows past the end of the sequence.  The second key tile (keys 128-255) of dV / dK reads a fourth "atom" that is
+// simply the memory after the third one (finite bf16 data): it only feeds accumulator rows >= 192 that no one stores.
+// Shared memory: P, dS 3 x 20 KB each | Q, dO, K, V 20 KB each (160 rows: a 128-row and a 32-row TMA box).
+constexpr int kSbMaxS = 160;
+constexpr int kSbOperand = 160 * 128;          // [160 rows][64] bf16, 128B-swizzled
+constexpr int kSbAtom = kSbOperand;            // one 64-key atom of P / dS: [160 query rows][64 keys]
+constexpr int kSbP = 0, kSbDS = 3 * kSbAtom, kSbQ = 6 * kSbAtom, kSbDO = kSbQ + kSbOperand, kSbK = kSbDO + kSbOperand,
+              kSbV = kSbK + kSbOperand, kSbBars = kSbV + kSbOperand;
+constexpr int kSbSmem = kSbBars + 256;
+static_assert(kSbSmem <= 232448, "small backward: shared memory");
+
+__global__ void __launch_bounds__(kSmThreads, 1)
+attn_small_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_qkv32,
+                      const __grid_constant__ CUtensorMap tm_do, const __grid_constant__ CUtensorMap tm_do32,
+                      const __grid_constant__ CUtensorMap tm_dqkv, const float* __restrict__ lse,
+                      const float* __restrict__ delta, int S, int H, int n_work, float scale) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kSbBars);
+  uint64_t* in_full = bars + 0;      // TMA -> MMA
+  uint64_t* in_free = bars + 1;      // MMA (commit) -> TMA: every MMA of the item has read its operands
+  uint64_t* sdp_full = bars + 2;     // [2] MMA -> compute: S_t / dP_t
+  uint64_t* sdp_free = bars + 4;     // [2] compute -> MMA: tile t's scores are in registers
+  uint64_t* pds_full = bars + 6;     // [2] compute -> MMA: P_t / dS_t are in shared memory
+  uint64_t* acc_full = bars + 8;     // MMA -> compute: dQ, dV, dK complete
+  uint64_t* acc_free = bars + 9;     // compute -> MMA: accumulators read
+  uint64_t* epi_full = bars + 10;    // compute -> store warp: output tiles staged
+  uint64_t* stage_free = bars + 11;  // store warp -> compute: staging (= P / dS buffers) read by the TMA stores
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int S16 = (S + 15) & ~15;
+  const int n_q = S > kTile ? 2 : 1;   // query tiles = key tiles
+  const int ksteps = S16 >> 4;
+  const int n_my = (n_work - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  auto item_bh = [&](int k) { return (int)blockIdx.x + k * (int)gridDim.x; };
+  const uint32_t sbase = smem_u32(smem);
+
+  if (threadIdx.x == 0) {
+    if ((sbase & 1023u) != 0) __trap();
+    tma_prefetch_desc(&tm_qkv);
+    tma_prefetch_desc(&tm_qkv32);
+    tma_prefetch_desc(&tm_do);
+    tma_prefetch_desc(&tm_do32);
+    tma_prefetch_desc(&tm_dqkv);
+    mbar_init(in_full, 1);
+    mbar_init(in_free, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&sdp_full[i], 1);
+      mbar_init(&sdp_free[i], 8);
+      mbar_init(&pds_full[i], 8);
+    }
+    mbar_init(acc_full, 1);
+    mbar_init(acc_free, 8);
+    mbar_init(epi_full, 8);
+    mbar_init(stage_free, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tS = tmem_base, tDP = tmem_base + 160, tDQ = tmem_base + 320;  // dQ_t at tDQ + 64 t
+  // end of item: dV_j at tmem_base + 64 j, dK_j at tmem_base + 128 + 64 j
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int k = 0; k < n_my; ++k) {
+        const int bh = item_bh(k), h = bh % H, b = bh / H;
+        if (k > 0) mbar_wait(in_free, (uint32_t)(k - 1) & 1u);
+        mbar_expect_tx(in_full, 4 * kTileBytes + (n_q == 2 ? 4 * 32 * 128 : 0));
+        tma_load_4d(smem + kSbQ, &tm_qkv, in_full, 0, h, 0, b);
+        tma_load_4d(smem + kSbDO, &tm_do, in_full, 0, h, 0, b);
+        tma_load_4d(smem + kSbK, &tm_qkv, in_full, 0, H + h, 0, b);
+        tma_load_4d(smem + kSbV, &tm_qkv, in_full, 0, 2 * H + h, 0, b);
+        if (n_q == 2) {  // rows 128 .. 159 (zero-filled past S)
+          tma_load_4d(smem + kSbQ + kTileBytes, &tm_qkv32, in_full, 0, h, kTile, b);
+          tma_load_4d(smem + kSbDO + kTileBytes, &tm_do32, in_full, 0, h, kTile, b);
+          tma_load_4d(smem + kSbK + kTileBytes, &tm_qkv32, in_full, 0, H + h, kTile, b);
+          tma_load_4d(smem + kSbV + kTileBytes, &tm_qkv32, in_full, 0, 2 * H + h, kTile, b);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc_s = umma_idesc_bf16(S16, 0, 0, 128);           // S, dP: A, B K-major, N = S16
+    constexpr uint32_t idesc_dq = umma_idesc_bf16(64, 0, 1, 128);       // dQ: A = dS K-major, B = K MN-major
+    constexpr uint32_t idesc_dkv = umma_idesc_bf16(64, 1, 1, 128);      // dV, dK: A = P^T / dS^T MN-major, B MN-major
+    for (int k = 0; k < n_my; ++k) {
+      mbar_wait(in_full, (uint32_t)k & 1u);
+      if (k > 0) mbar_wait(acc_free, (uint32_t)(k - 1) & 1u);  // S / dP overwrite the previous item's dV / dK columns
+      for (int t = 0; t < n_q; ++t) {
+        if (t > 0) mbar_wait(&sdp_free[t - 1], (uint32_t)k & 1u);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint64_t dQ = desc_k(sbase + kSbQ + t * kTileBytes, 0), dK = desc_k(sbase + kSbK, 0);
+          const uint64_t dO = desc_k(sbase + kSbDO + t * kTileBytes, 0), dV = desc_k(sbase + kSbV, 0);
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) umma_bf16_ss(tS, dQ + 2 * kk, dK + 2 * kk, idesc_s, kk > 0);
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) umma_bf16_ss(tDP, dO + 2 * kk, dV + 2 * kk, idesc_s, kk > 0);
+          umma_commit(&sdp_full[t]);
+        }
+        __syncwarp();
+      }
+      for (int t = 0; t < n_q; ++t) {
+        mbar_wait(&pds_full[t], (uint32_t)k & 1u);
+        tc_fence_after();
+        if (elect_one()) {
+          // dQ_t = dS_t K: A rows = tile t's queries, k-step kk = keys 16 kk .. : atom kk / 4, 32 bytes per step inside it
+          for (int kk = 0; kk < ksteps; ++kk) {
+            const uint64_t dA = umma_smem_desc(sbase + kSbDS + (kk >> 2) * kSbAtom + t * kTileBytes + (kk & 3) * 32, 1024, 16);
+            const uint64_t dB = umma_smem_desc(sbase + kSbK + kk * 2048, 1024, 8192);
+            umma_bf16_ss(tDQ + (uint32_t)t * 64, dA, dB, idesc_dq, kk > 0);
+          }
+        }
+        __syncwarp();
+      }
+      // every tile's scores have been read (pds_full follows the loads): dV_j / dK_j may take the S / dP columns
+      if (elect_one()) {
+        for (int j = 0; j < n_q; ++j) {
+          for (int kk = 0; kk < ksteps; ++kk) {  // k = queries, 16 rows = 2048 bytes per step
+            const uint64_t aP = umma_smem_desc(sbase + kSbP + 2 * j * kSbAtom + kk * 2048, 1024, kSbAtom);
+            const uint64_t bO = umma_smem_desc(sbase + kSbDO + kk * 2048, 1024, 8192);
+            umma_bf16_ss(tmem_base + (uint32_t)j * 64, aP, bO, idesc_dkv, kk > 0);
+          }
+          for (int kk = 0; kk < ksteps; ++kk) {
+            const uint64_t aS = umma_smem_desc(sbase + kSbDS + 2 * j * kSbAtom + kk * 2048, 1024, kSbAtom);
+            const uint64_t bQ = umma_smem_desc(sbase + kSbQ + kk * 2048, 1024, 8192);
+            umma_bf16_ss(tmem_base + 128 + (uint32_t)j * 64, aS, bQ, idesc_dkv, kk > 0);
+          }
+        }
+        umma_commit(acc_full);
+        umma_commit(in_free);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 2) {
+    for (int k = 0; k < n_my; ++k) {
+      const int bh = item_bh(k), h = bh % H, b = bh / H;
+      mbar_wait(epi_full, (uint32_t)k & 1u);
+      if (lane == 0) {
+        for (int j = 0; j < n_q; ++j) {  // staging tiles: dQ_j, dV_j, dK_j at 3 j, 3 j + 1, 3 j + 2
+          tma_store_4d(&tm_dqkv, smem + (3 * j + 0) * kTileBytes, 0, h, j * kTile, b);
+          tma_store_4d(&tm_dqkv, smem + (3 * j + 1) * kTileBytes, 0, 2 * H + h, j * kTile, b);
+          tma_store_4d(&tm_dqkv, smem + (3 * j + 2) * kTileBytes, 0, H + h, j * kTile, b);
+        }
+        tma_store_commit();
+        tma_store_wait_read0();
+        mbar_arrive(stage_free);
+      }
+      __syncwarp();
+    }
+    if (lane == 0) tma_store_wait0();
+  } else if (warp >= 4) {
+    const int q4 = warp & 3, hh = (warp - 4) >> 2;
+    const int row = q4 * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(q4 * 32) << 16;
+    const int Wh = S16 >> 1;  // columns per half (multiple of 8)
+    const float c_log2 = scale * kLog2e;
+    const uint64_t cl2 = pack2(c_log2, c_log2), sc2 = pack2(scale, scale);
+    for (int k = 0; k < n_my; ++k) {
+      const int bh = item_bh(k);
+      if (k > 0) mbar_wait(stage_free, (uint32_t)(k - 1) & 1u);  // the previous item's stores have read P / dS space
+      for (int t = 0; t < n_q; ++t) {
+        const bool live = t * kTile + q4 * 32 < S;
+        const int r = t * kTile + row;  // query row = row of the P / dS atoms
+        float nl = 0.f, nd = 0.f;
+        if (live) {
+          const long long o = (long long)bh * S + min(r, S - 1);
+          nl = -__ldg(lse + o) * kLog2e;
+          nd = -__ldg(delta + o) * scale;
+        }
+        const uint64_t nl2 = pack2(nl, nl), nd2 = pack2(nd, nd);
+        mbar_wait(&sdp_full[t], (uint32_t)k & 1u);
+        tc_fence_after();
+        if (live) {
+          for (int c0 = hh * Wh; c0 < (hh + 1) * Wh; c0 += 16) {
+            const bool two = c0 + 16 <= (hh + 1) * Wh;  // 16 columns, or a last group of 8
+            uint32_t sv[2][8], dv[2][8];
+            tmem_ld_32x32b_x8(tS + lane_base + c0, sv[0]);
+            tmem_ld_32x32b_x8(tDP + lane_base + c0, dv[0]);
+            if (two) {
+              tmem_ld_32x32b_x8(tS + lane_base + c0 + 8, sv[1]);
+              tmem_ld_32x32b_x8(tDP + lane_base + c0 + 8, dv[1]);
+            }
+            tmem_ld_wait();
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              if (u == 1 && !two) break;
+              uint32_t pk[4], dk[4];
+#pragma unroll
+              for (int i = 0; i < 8; i += 2) {
+                const uint64_t s2 = pack2(__uint_as_float(sv[u][i]), __uint_as_float(sv[u][i + 1]));
+                const uint64_t p2 = pack2(__uint_as_float(dv[u][i]), __uint_as_float(dv[u][i + 1]));
+                const uint64_t e2 = exp2_mufu2(ffma2(s2, cl2, nl2));
+                float p0, p1, d0, d1;
+                unpack2(e2, p0, p1);
+                unpack2(fmul2(e2, ffma2(p2, sc2, nd2)), d0, d1);
+                pk[i >> 1] = pack_bf16x2(p0, p1);
+                dk[i >> 1] = pack_bf16x2(d0, d1);
+              }
+              const int col = c0 + 8 * u;  // 8 keys = one 16-byte chunk of the 128B-swizzled row
+              const uint32_t off = (uint32_t)((col >> 6) * kSbAtom + r * 128 + ((((col & 63) >> 3) ^ (r & 7)) << 4));
+              sts_u4(sbase + kSbP + off, pk[0], pk[1], pk[2], pk[3]);
+              sts_u4(sbase + kSbDS + off, dk[0], dk[1], dk[2], dk[3]);
+            }
+          }
+        }
+        tc_fence_before();
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&sdp_free[t]);
+          mbar_arrive(&pds_full[t]);
+        }
+      }
+      // drain: dQ_j, dV_j, dK_j -> bf16 -> staging tiles 3 j, 3 j + 1, 3 j + 2 (over the dead P / dS buffers)
+      mbar_wait(acc_full, (uint32_t)k & 1u);
+      tc_fence_after();
+      for (int j = 0; j < n_q; ++j) {
+        if (j * kTile + q4 * 32 >= S) continue;  // rows the stores clip
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+          const uint32_t tacc = a == 0 ? tDQ + (uint32_t)j * 64
+                                       : (a == 1 ? tmem_base + (uint32_t)j * 64 : tmem_base + 128 + (uint32_t)j * 64);
+          uint32_t ov[32];
+          tmem_ld_32x32b_x32(tacc + lane_base + hh * 32, ov);
+          tmem_ld_wait();
+          const uint32_t dst = sbase + (uint32_t)(3 * j + a) * kTileBytes + row * 128;
+#pragma unroll
+          for (int gq = 0; gq < 4; ++gq)
+            sts_u4(dst + (((hh * 4 + gq) ^ (row & 7)) << 4),
+                   pack_bf16x2(__uint_as_float(ov[gq * 8 + 0]), __uint_as_float(ov[gq * 8 + 1])),
+                   pack_bf16x2(__uint_as_float(ov[gq * 8 + 2]), __uint_as_float(ov[gq * 8 + 3])),
+                   pack_bf16x2(__uint_as_float(ov[gq * 8 + 4]), __uint_as_float(ov[gq * 8 + 5])),
+                   pack_bf16x2(__uint_as_float(ov[gq * 8 + 6]), __uint_as_float(ov[gq * 8 + 7])));
+        }
+      }
+      tc_fence_before();
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(acc_free);
+        mbar_arrive(epi_full);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+int attn_small_bwd_launch(const void* qkv, const void* dout, const float* lse, const float* delta, int B, int S, int H,
+                          float scale, void* dqkv, cudaStream_t st) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    if (cudaFuncSetAttribute(attn_small_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSbSmem) != cudaSuccess)
+      return BVC_ERR_LAUNCH;
+    attr_done = true;
+  }
+  BVC_CHECK_ARG(S <= kSbMaxS);
+  CUtensorMap tq, tq32, td, td32, tdq;
+  if (make_head_tmap(&tq, qkv, 3 * H, S, B) || make_head_tmap(&tq32, qkv, 3 * H, S, B, 32) ||
+      make_head_tmap(&td, dout, H, S, B) || make_head_tmap(&td32, dout, H, S, B, 32) ||
+      make_head_tmap(&tdq, dqkv, 3 * H, S, B))
+    return BVC_ERR_DRIVER;
+  const long long n_work = (long long)B * H;
+  BVC_CHECK_ARG(n_work < (1ll << 30));
+  const int grid = (int)(n_work < num_sms() ? n_work : num_sms());
+  attn_small_bwd_kernel<<<grid, kSmThreads, kSbSmem, st>>>(tq, tq32, td, td32, tdq, lse, delta, S, H, (int)n_work, scale);
+  BVC_CHECK_LAUNCH();
+  return BVC_OK;
+}
+
 int attn_small_fwd_launch(const void* qkv, int B, int S, int H, float scale, void* out, float* lse, cudaStream_t st) {
   static bool attr_done = false;
   if (!attr_done) {

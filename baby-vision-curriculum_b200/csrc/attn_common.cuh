@@ -49,6 +49,13 @@ __device__ __forceinline__ void tmem_ld_32x32b_x8(uint32_t taddr, uint32_t (&v)[
                : "r"(taddr)
                : "memory");
 }
+// Placed right after tcgen05.wait::ld: names the loaded registers as read-write operands of (empty) volatile asm
+// statements, which keep their order after the wait -- so nothing that consumes them can be scheduled above it.
+template <int N>
+__device__ __forceinline__ void tmem_ld_pin(uint32_t (&v)[N]) {
+#pragma unroll
+  for (int i = 0; i < N; ++i) asm volatile("" : "+r"(v[i]));
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // K-major operand tile [rows][64]: k-step (16 elements) = +32 bytes inside the swizzle atom

@@ -166,6 +166,7 @@ attn_small_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_c
           uint32_t v[32];
           tmem_ld_32x32b_x32(mS + c * 32, v);
           tmem_ld_wait();
+          tmem_ld_pin(v);
           if (c * 32 + 32 <= S) {
             float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
@@ -181,6 +182,7 @@ attn_small_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_c
           uint32_t v[16];
           tmem_ld_32x32b_x16(mS + n32 * 32, v);
           tmem_ld_wait();
+          tmem_ld_pin(v);
 #pragma unroll
           for (int i = 0; i < 16; ++i)
             if (n32 * 32 + i < S) mx = fmaxf(mx, __uint_as_float(v[i]));
@@ -194,6 +196,7 @@ attn_small_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_c
           uint32_t v[32], pk[16];
           tmem_ld_32x32b_x32(mS + c * 32, v);
           tmem_ld_wait();
+          tmem_ld_pin(v);
           if (c * 32 + 32 <= S) {
 #pragma unroll
             for (int i = 0; i < 32; i += 2) {
@@ -225,6 +228,7 @@ attn_small_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_c
           uint32_t v[16], pk[8];
           tmem_ld_32x32b_x16(mS + n32 * 32, v);
           tmem_ld_wait();
+          tmem_ld_pin(v);
 #pragma unroll
           for (int i = 0; i < 16; i += 2) {
             float p0, p1;
@@ -250,6 +254,7 @@ attn_small_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_c
           uint32_t ov[32];
           tmem_ld_32x32b_x32(mO + c * 32, ov);
           tmem_ld_wait();
+          tmem_ld_pin(ov);
 #pragma unroll
           for (int gq = 0; gq < 4; ++gq) {
             uint4 o4;
@@ -468,16 +473,26 @@ attn_small_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_c
         mbar_wait(&sdp_full[t], (uint32_t)k & 1u);
         tc_fence_after();
         if (live) {
-          for (int c0 = hh * Wh; c0 < (hh + 1) * Wh; c0 += 16) {
-            const bool two = c0 + 16 <= (hh + 1) * Wh;  // 16 columns, or a last group of 8
-            uint32_t sv[2][8], dv[2][8];
+          // groups of 16 columns (a last group may have 8); the TMEM loads of group g + 1 are in flight while group g
+          // is computed and stored (two named register sets: a dynamically indexed one would live in local memory)
+          const int c_end = (hh + 1) * Wh;
+          uint32_t svA[2][8], dvA[2][8], svB[2][8], dvB[2][8];
+          auto issue = [&](int c0, uint32_t (&sv)[2][8], uint32_t (&dv)[2][8]) {
             tmem_ld_32x32b_x8(tS + lane_base + c0, sv[0]);
             tmem_ld_32x32b_x8(tDP + lane_base + c0, dv[0]);
-            if (two) {
+            if (c0 + 16 <= c_end) {
               tmem_ld_32x32b_x8(tS + lane_base + c0 + 8, sv[1]);
               tmem_ld_32x32b_x8(tDP + lane_base + c0 + 8, dv[1]);
             }
-            tmem_ld_wait();
+          };
+          auto compute = [&](int c0, uint32_t (&sv)[2][8], uint32_t (&dv)[2][8]) {
+            const bool two = c0 + 16 <= c_end;
+            tmem_ld_pin(sv[0]);
+            tmem_ld_pin(dv[0]);
+            if (two) {
+              tmem_ld_pin(sv[1]);
+              tmem_ld_pin(dv[1]);
+            }
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
               if (u == 1 && !two) break;
@@ -497,6 +512,17 @@ attn_small_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_c
               const uint32_t off = (uint32_t)((col >> 6) * kSbAtom + r * 128 + ((((col & 63) >> 3) ^ (r & 7)) << 4));
               sts_u4(sbase + kSbP + off, pk[0], pk[1], pk[2], pk[3]);
               sts_u4(sbase + kSbDS + off, dk[0], dk[1], dk[2], dk[3]);
+            }
+          };
+          issue(hh * Wh, svA, dvA);
+          for (int c0 = hh * Wh; c0 < c_end; c0 += 32) {
+            tmem_ld_wait();
+            if (c0 + 16 < c_end) issue(c0 + 16, svB, dvB);
+            compute(c0, svA, dvA);
+            if (c0 + 16 < c_end) {
+              tmem_ld_wait();
+              if (c0 + 32 < c_end) issue(c0 + 32, svA, dvA);
+              compute(c0 + 16, svB, dvB);
             }
           }
         }
@@ -520,6 +546,7 @@ attn_small_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_c
           uint32_t ov[32];
           tmem_ld_32x32b_x32(tacc + lane_base + hh * 32, ov);
           tmem_ld_wait();
+          tmem_ld_pin(ov);
           const uint32_t dst = sbase + (uint32_t)(3 * j + a) * kTileBytes + row * 128;
 #pragma unroll
           for (int gq = 0; gq < 4; ++gq)

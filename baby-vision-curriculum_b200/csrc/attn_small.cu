@@ -316,7 +316,7 @@ attn_small_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_c
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kSbBars);
   uint64_t* in_full = bars + 0;      // TMA -> MMA
-  uint64_t* in_free = bars + 1;      // MMA (commit) -> TMA: every MMA of the item has read its operands
+  uint64_t* k_free = bars + 1;       // MMA (commit) -> TMA: K's last reader (dQ of the last tile, the item's last MMAs) is done
   uint64_t* sdp_full = bars + 2;     // [2] MMA -> compute: S_t / dP_t
   uint64_t* sdp_free = bars + 4;     // [2] compute -> MMA: tile t's scores are in registers
   uint64_t* pds_full = bars + 6;     // [2] compute -> MMA: P_t / dS_t are in shared memory
@@ -324,7 +324,9 @@ attn_small_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_c
   uint64_t* acc_free = bars + 9;     // compute -> MMA: accumulators read
   uint64_t* epi_full = bars + 10;    // compute -> store warp: output tiles staged
   uint64_t* stage_free = bars + 11;  // store warp -> compute: staging (= P / dS buffers) read by the TMA stores
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  uint64_t* v_free = bars + 12;      // MMA (commit) -> TMA: V's last reader (dP of the last tile) is done
+  uint64_t* qdo_free = bars + 13;    // MMA (commit) -> TMA: Q's and dO's last readers (dK, dV) are done
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int S16 = (S + 15) & ~15;
@@ -342,7 +344,9 @@ attn_small_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_c
     tma_prefetch_desc(&tm_do32);
     tma_prefetch_desc(&tm_dqkv);
     mbar_init(in_full, 1);
-    mbar_init(in_free, 1);
+    mbar_init(k_free, 1);
+    mbar_init(v_free, 1);
+    mbar_init(qdo_free, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&sdp_full[i], 1);
       mbar_init(&sdp_free[i], 8);
@@ -366,18 +370,24 @@ attn_small_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_c
     if (lane == 0) {
       for (int k = 0; k < n_my; ++k) {
         const int bh = item_bh(k), h = bh % H, b = bh / H;
-        if (k > 0) mbar_wait(in_free, (uint32_t)(k - 1) & 1u);
+        // each operand of item k is fetched as soon as its last reader of item k - 1 has finished -- V after the last
+        // dP, Q / dO after dK / dV, K after the last dQ -- instead of all four after the item's last MMA: the loads of
+        // the 148 CTAs, which run in lockstep, no longer hit L2 as one 12 MB burst that nothing overlaps
+        const uint32_t ph = (uint32_t)(k - 1) & 1u;
+        if (k > 0) mbar_wait(v_free, ph);
         mbar_expect_tx(in_full, 4 * kTileBytes + (n_q == 2 ? 4 * 32 * 128 : 0));
+        tma_load_4d(smem + kSbV, &tm_qkv, in_full, 0, 2 * H + h, 0, b);
+        if (n_q == 2) tma_load_4d(smem + kSbV + kTileBytes, &tm_qkv32, in_full, 0, 2 * H + h, kTile, b);
+        if (k > 0) mbar_wait(qdo_free, ph);
         tma_load_4d(smem + kSbQ, &tm_qkv, in_full, 0, h, 0, b);
         tma_load_4d(smem + kSbDO, &tm_do, in_full, 0, h, 0, b);
-        tma_load_4d(smem + kSbK, &tm_qkv, in_full, 0, H + h, 0, b);
-        tma_load_4d(smem + kSbV, &tm_qkv, in_full, 0, 2 * H + h, 0, b);
         if (n_q == 2) {  // rows 128 .. 159 (zero-filled past S)
           tma_load_4d(smem + kSbQ + kTileBytes, &tm_qkv32, in_full, 0, h, kTile, b);
           tma_load_4d(smem + kSbDO + kTileBytes, &tm_do32, in_full, 0, h, kTile, b);
-          tma_load_4d(smem + kSbK + kTileBytes, &tm_qkv32, in_full, 0, H + h, kTile, b);
-          tma_load_4d(smem + kSbV + kTileBytes, &tm_qkv32, in_full, 0, 2 * H + h, kTile, b);
         }
+        if (k > 0) mbar_wait(k_free, ph);
+        tma_load_4d(smem + kSbK, &tm_qkv, in_full, 0, H + h, 0, b);
+        if (n_q == 2) tma_load_4d(smem + kSbK + kTileBytes, &tm_qkv32, in_full, 0, H + h, kTile, b);
       }
     }
   } else if (warp == 1) {
@@ -398,23 +408,28 @@ attn_small_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_c
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) umma_bf16_ss(tDP, dO + 2 * kk, dV + 2 * kk, idesc_s, kk > 0);
           umma_commit(&sdp_full[t]);
+          if (t == n_q - 1) umma_commit(v_free);  // V's last reader
         }
         __syncwarp();
       }
+      // dQ_t = dS_t K: A rows = tile t's queries, k-step kk = keys 16 kk .. : atom kk / 4, 32 bytes per step inside it
+      auto issue_dq = [&](int t) {
+        for (int kk = 0; kk < ksteps; ++kk) {
+          const uint64_t dA = umma_smem_desc(sbase + kSbDS + (kk >> 2) * kSbAtom + t * kTileBytes + (kk & 3) * 32, 1024, 16);
+          const uint64_t dB = umma_smem_desc(sbase + kSbK + kk * 2048, 1024, 8192);
+          umma_bf16_ss(tDQ + (uint32_t)t * 64, dA, dB, idesc_dq, kk > 0);
+        }
+      };
       for (int t = 0; t < n_q; ++t) {
         mbar_wait(&pds_full[t], (uint32_t)k & 1u);
         tc_fence_after();
-        if (elect_one()) {
-          // dQ_t = dS_t K: A rows = tile t's queries, k-step kk = keys 16 kk .. : atom kk / 4, 32 bytes per step inside it
-          for (int kk = 0; kk < ksteps; ++kk) {
-            const uint64_t dA = umma_smem_desc(sbase + kSbDS + (kk >> 2) * kSbAtom + t * kTileBytes + (kk & 3) * 32, 1024, 16);
-            const uint64_t dB = umma_smem_desc(sbase + kSbK + kk * 2048, 1024, 8192);
-            umma_bf16_ss(tDQ + (uint32_t)t * 64, dA, dB, idesc_dq, kk > 0);
-          }
+        if (t < n_q - 1) {  // the first tile's dQ runs under the second tile's math
+          if (elect_one()) issue_dq(t);
+          __syncwarp();
         }
-        __syncwarp();
       }
-      // every tile's scores have been read (pds_full follows the loads): dV_j / dK_j may take the S / dP columns
+      // every tile's scores have been read (pds_full follows the loads): dV_j / dK_j may take the S / dP columns; the
+      // last tile's dQ goes after them, so that Q / dO (two of the four operands) are released before the item's end
       if (elect_one()) {
         for (int j = 0; j < n_q; ++j) {
           for (int kk = 0; kk < ksteps; ++kk) {  // k = queries, 16 rows = 2048 bytes per step
@@ -428,8 +443,10 @@ attn_small_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_c
             umma_bf16_ss(tmem_base + 128 + (uint32_t)j * 64, aS, bQ, idesc_dkv, kk > 0);
           }
         }
+        umma_commit(qdo_free);
+        issue_dq(n_q - 1);
         umma_commit(acc_full);
-        umma_commit(in_free);
+        umma_commit(k_free);
       }
       __syncwarp();
     }

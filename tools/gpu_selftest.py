@@ -360,6 +360,10 @@ def run_attn():
     attn_case(2, 100, 1)
     attn_case(2, 129, 2)
     attn_case(40, 160, 12)
+    attn_case(2, 2, 1)   # (S = 1 has an exactly-zero dq / dk reference: no relative error to take)
+    attn_case(2, 17, 2)
+    attn_case(1, 33, 1)
+    attn_case(3, 159, 2)
 
 
 # ------------------------------------------------------------------------------------------------ perf probes

@@ -12,7 +12,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libbvc.so")
-ABI_VERSION = 11
+ABI_VERSION = 12
 
 _lib = None
 
@@ -38,6 +38,7 @@ class GemmArgs(C.Structure):
 
 _SIGNATURES = {
     "bvc_abi_version": (C.c_int, []),
+    "bvc_set_sm_limit": (C.c_int, [C.c_int32]),
     "bvc_mask_count": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "bvc_mask_to_index": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_void_p]),
@@ -447,3 +448,8 @@ def ema_update(table, n_entries, momentum, total_elems):
     with _Timed("ema_update", 0.0, float(total_elems) * 12):
         _check(load().bvc_ema_update(_p(table), n_entries, float(momentum), _stream()), "bvc_ema_update")
     _count()
+
+
+def set_sm_limit(n_sms):
+    """Size the persistent kernels' grids for n_sms SMs (0 = all); returns the previous setting."""
+    return int(load().bvc_set_sm_limit(int(n_sms)))

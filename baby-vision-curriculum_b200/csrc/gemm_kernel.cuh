@@ -758,7 +758,9 @@ static int launch_gemm(const bvc_gemm_args* a, cudaStream_t stream) {
                   a->res == nullptr && a->target == nullptr);
   }
   const long long total = (long long)p.tiles_m * p.tiles_n * p.k_splits;
-  const int workers = (int)(total < max_workers ? total : max_workers);
+  int cap = PAIR ? num_sms() / 2 : num_sms();  // honours bvc_set_sm_limit at every launch
+  if (cap > max_workers) cap = max_workers;
+  const int workers = (int)(total < cap ? total : cap);
   if constexpr (PAIR != 0) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * workers);

@@ -17,6 +17,7 @@ broadcast from rank 0 at construction like DDP's _sync_module_states.
 from __future__ import annotations
 
 import contextlib
+import os
 
 import torch
 import torch.distributed as dist
@@ -37,6 +38,15 @@ class GradSync:
         backend = dist.get_backend(process_group)
         self._avg = backend == "nccl"   # gloo (CPU tests) has no AVG: SUM then scale
         self.launched = 0               # collectives launched (bench / tests)
+        # SMs left to NCCL while all-reduces are in flight (BVC_DDP_SM_RESERVE, default NCCL_MAX_CTAS if that is set):
+        # the persistent kernels of the rest of the backward size their grids for the remaining SMs instead of
+        # running their last CTAs, and those CTAs' share of the work, as a second wave (include/bvc.h bvc_set_sm_limit)
+        self._sm_limit = 0
+        if backend == "nccl" and torch.cuda.is_available():
+            reserve = int(os.environ.get("BVC_DDP_SM_RESERVE", os.environ.get("NCCL_MAX_CTAS", "0")) or 0)
+            n = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
+            if 0 < reserve < n // 2:
+                self._sm_limit = n - reserve
 
     def reduce(self, flat: torch.Tensor):
         if not self.enabled or self.world == 1:
@@ -45,6 +55,9 @@ class GradSync:
             # first bucket of this backward pass: have the engine call us when the pass is over
             torch.autograd.Variable._execution_engine.queue_callback(self._finalize)
             self._armed = True
+            if self._sm_limit:
+                from . import _lib as L
+                L.set_sm_limit(self._sm_limit)
         if self.deferred:
             return  # autograd will ADD this stage's gradients into existing .grad tensors: reduce those at the end
         self._launch(flat)
@@ -66,6 +79,9 @@ class GradSync:
                 if p.grad is not None:
                     self._launch(p.grad)
         works, self._works, self._armed = self._works, [], False
+        if self._sm_limit:
+            from . import _lib as L
+            L.set_sm_limit(0)
         for w, flat in works:
             w.wait()  # stream-level on CUDA: the host does not block
             if not self._avg:

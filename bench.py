@@ -191,6 +191,12 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # Optional (BVC_BENCH_NCCL_TUNE=1): cap NCCL at 8 CTAs and let bvc.DistributedDataParallel size the persistent
+        # kernels of the backward for the remaining SMs while all-reduces are in flight.  Measured on 8 x B200: 26.51 ms
+        # per step against 26.16 ms with NCCL's defaults in the same job -- not a win, so it is off by default.
+        if os.environ.get("BVC_BENCH_NCCL_TUNE", "0") == "1":
+            os.environ.setdefault("NCCL_MAX_CTAS", "8")
+            os.environ.setdefault("BVC_DDP_SM_RESERVE", os.environ["NCCL_MAX_CTAS"])
         dist.init_process_group("nccl", device_id=dev)
     c = CONFIGS[args.config]
     B = args.batch

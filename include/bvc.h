@@ -28,10 +28,14 @@ extern "C" {
 #define BVC_ERR_ARG (-1)
 #define BVC_ERR_DRIVER (-2)
 #define BVC_ERR_LAUNCH (-3)
-#define BVC_ABI_VERSION 11
+#define BVC_ABI_VERSION 12
 
 /* library / build info: returns BVC_ABI_VERSION (bumped when a signature changes) */
 int bvc_abi_version(void);
+/* Size the persistent kernels' grids for n_sms SMs instead of all of them (0 = all); returns the previous setting.
+ * Host-side state, read at every launch.  bvc_b200.DistributedDataParallel lowers it by the number of CTAs NCCL may
+ * hold (NCCL_MAX_CTAS) while the gradient all-reduces of a backward pass are in flight. */
+int bvc_set_sm_limit(int32_t n_sms);
 
 /* ------------------------------------------------------------------------------------------------------
  * Tube-mask indexing.  Replaces the boolean-index ops `x[~bool_masked_pos]` / `x[bool_masked_pos]`

@@ -739,7 +739,6 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
     const int q4 = warp & 3;
     const int half = e >> 2;
     const int row = q4 * 32 + lane;
-    const int ct = threadIdx.x - 128;  // 0..255
     const uint32_t lane_base = (uint32_t)(q4 * 32) << 16;
     const float c_log2 = scale * kLog2e;
     const uint64_t cl2 = pack2(c_log2, c_log2), sc2 = pack2(scale, scale);
@@ -754,7 +753,6 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
     if (!MODE_KV && n_glob > 0) load_row(0, l_cur, d_cur);
     int g = 0;
     for (int k = 0; k < n_my; ++k) {
-      const int own0 = item_tile(k) * kTile, bh = item_bh(k), h = bh % H, b = bh / H;
       uint64_t nl2 = 0, nd2 = 0;
       float l_nxt = 0.f, d_nxt = 0.f;
       if (!MODE_KV) {

@@ -201,11 +201,8 @@ def run_ours(args):
     c = CONFIGS[args.config]
     B = args.batch
     sampler = ClockSampler(local)  # started now: nvidia-smi's NVML initialisation is over long before the timed steps
-    if rank == 0 and os.environ.get("BVC_BENCH_NO_SAMPLER", "0") != "1":
+    if rank == 0:
         sampler.start()
-    if os.environ.get("BVC_BENCH_GC", "") == "off":
-        import gc
-        gc.disable()
     torch.manual_seed(0)
     model = bvc.VideoMAEForPreTraining(bvc.VideoMAEConfig(**c)).to(dev).train()
     xmodel = model

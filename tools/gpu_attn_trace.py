@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Per-phase SM-clock trace of the attention pipelines (CTA 0; mode 1 = backward KV pass, 0 = backward Q pass,
 2 = forward: columns are wait S | LDTM | max + rescale | exp + pack | STTM for softmax group 0): builds csrc/attn.cu with -DBVC_TRACE into
-libbvc_trace.so (done on the build box: `nvcc ... -DBVC_TRACE -shared csrc/attn.cu -o libbvc_trace.so`), runs one
+libbvc_trace.so (done on the build box: `nvcc ... -DBVC_TRACE -shared csrc/attn.cu csrc/attn_small.cu -o libbvc_trace.so`; set BVC_ATTN_SMALL=0 to
+trace the general kernels at S <= 192), runs one
 pass and prints, per streamed tile, how long each role spent in each phase.
     python tools/gpu_attn_trace.py B S H mode_kv
 """

@@ -183,3 +183,95 @@ def ema_update(encoder_params, target_params, m):
             _ema_tables.clear()
         _ema_tables[key] = hit
     L.ema_update(hit[0], hit[1], float(m), hit[2])
+
+
+# ------------------------------------------------------------------------------------------------ host side: masks
+# The predictive path's masks are made on the host, in the DataLoader's collate function, and shifted to a temporal slot
+# before they reach the device.  Mirrors with the reference's names, arguments and random-number
+# consumption, so a seeded run produces the same index tensors (tests/test_jepa_oracle.py pins them on fixtures made by
+# the reference's own classes).
+def update_masks(masks, image_size, patch_size, num_frames, tubelet_size, isencoder=False):
+    """pretraining/predictive/mask.py:21-38: per-frame patch indices -> spatio-temporal token indices.  Context masks
+    stay in the first temporal slot, prediction masks move to the last one (T - 1).  In place, like the reference."""
+    per_frame = (image_size // patch_size) ** 2
+    slot = 0 if isencoder else num_frames // tubelet_size - 1
+    for i, m in enumerate(masks):
+        m += slot * per_frame
+        masks[i] = m
+    return masks
+
+
+class MaskCollator(object):
+    """pretraining/predictive/mask.py:70-219 (the multi-block collator of pretrain_jepa.py:226-235): per batch one
+    prediction-block size and one context-block size from a generator seeded with a counter shared by the DataLoader
+    workers; per sample `npred` prediction blocks and `nenc` context blocks at uniformly random corners (global torch
+    RNG), the context blocks restricted to the complement of the sample's prediction blocks unless `allow_overlap`;
+    every mask truncated to the shortest one of the batch.  Returns (collated batch, masks_enc, masks_pred) with
+    masks_* = list of int64 [B, K] tensors of kept patch indices in ascending order."""
+
+    def __init__(self, input_size=(224, 224), patch_size=16, enc_mask_scale=(0.2, 0.8), pred_mask_scale=(0.2, 0.8),
+                 aspect_ratio=(0.3, 3.0), nenc=1, npred=2, min_keep=4, allow_overlap=False):
+        from multiprocessing import Value
+        if not isinstance(input_size, tuple):
+            input_size = (input_size,) * 2
+        self.patch_size = patch_size
+        self.height, self.width = input_size[0] // patch_size, input_size[1] // patch_size
+        self.enc_mask_scale, self.pred_mask_scale, self.aspect_ratio = enc_mask_scale, pred_mask_scale, aspect_ratio
+        self.nenc, self.npred, self.min_keep, self.allow_overlap = nenc, npred, min_keep, allow_overlap
+        self._itr_counter = Value("i", -1)   # shared across worker processes
+
+    def step(self):
+        with self._itr_counter.get_lock():
+            self._itr_counter.value += 1
+            return self._itr_counter.value
+
+    def _block_size(self, generator, scale, aspect_ratio_scale):
+        import math
+        u = torch.rand(1, generator=generator).item()          # ONE draw serves scale and aspect ratio (mask.py:104-112)
+        keep = int(self.height * self.width * (scale[0] + u * (scale[1] - scale[0])))
+        ar = aspect_ratio_scale[0] + u * (aspect_ratio_scale[1] - aspect_ratio_scale[0])
+        h = min(int(round(math.sqrt(keep * ar))), self.height - 1)
+        w = min(int(round(math.sqrt(keep / ar))), self.width - 1)
+        return h, w
+
+    def _block(self, size, forbidden=None):
+        """One block of `size` at a random corner -> (kept indices, its rectangle).  `forbidden`: rectangles the block
+        must avoid; after every 20 failed draws the LAST rectangle of the list is dropped (mask.py:126-150)."""
+        h, w = size
+        tries, budget = 0, 20
+        grid = torch.arange(self.height * self.width).view(self.height, self.width)
+        while True:
+            top = int(torch.randint(0, self.height - h, (1,)))
+            left = int(torch.randint(0, self.width - w, (1,)))
+            keep = torch.zeros((self.height, self.width), dtype=torch.bool)
+            keep[top:top + h, left:left + w] = True
+            if forbidden is not None:
+                for (t, l, hh, ww) in forbidden[:max(len(forbidden) - tries, 0)]:
+                    keep[t:t + hh, l:l + ww] = False
+            idx = grid[keep]                                      # row-major = ascending, what nonzero() returns
+            if len(idx) > self.min_keep:
+                return idx, (top, left, h, w)
+            budget -= 1
+            if budget == 0:
+                tries += 1
+                budget = 20
+
+    def __call__(self, batch):
+        B = len(batch)
+        collated = torch.utils.data.default_collate(batch)
+        g = torch.Generator()
+        g.manual_seed(self.step())
+        p_size = self._block_size(g, self.pred_mask_scale, self.aspect_ratio)
+        e_size = self._block_size(g, self.enc_mask_scale, (1., 1.))
+        pred, enc = [], []
+        for _ in range(B):
+            blocks = [self._block(p_size) for _ in range(self.npred)]
+            pred.append([b[0] for b in blocks])
+            forbidden = None if self.allow_overlap else [b[1] for b in blocks]
+            enc.append([self._block(e_size, forbidden)[0] for _ in range(self.nenc)])
+        kp = min(min(len(m) for m in ms) for ms in pred)
+        ke = min(min(len(m) for m in ms) for ms in enc)
+        kp, ke = min(kp, self.height * self.width), min(ke, self.height * self.width)
+        masks_pred = torch.utils.data.default_collate([[m[:kp] for m in ms] for ms in pred])
+        masks_enc = torch.utils.data.default_collate([[m[:ke] for m in ms] for ms in enc])
+        return collated, masks_enc, masks_pred

@@ -43,3 +43,23 @@ def test_jepa_oracle_matches_reference_fixtures(tag):
     new = J.ema_update(q, k, float(g["momentum"]))
     for i, kn in enumerate(new):
         assert torch.equal(kn, torch.from_numpy(g[f"ema_k{i}"]))
+
+
+@pytest.mark.parametrize("tag,B,seed", [("tiny", 2, 5), ("vitb", 4, 6)])
+def test_mask_collator_mirror_reproduces_the_reference_masks(tag, B, seed):
+    """bvc_b200.MaskCollator / update_masks (host side of the JEPA path, predictive/mask.py:21-38, :70-219) consume the
+    random numbers exactly like the reference's classes: the same seed gives the index tensors the fixture generator
+    got from the reference (tools/make_golden_jepa.py: torch.manual_seed(seed), first call of a fresh collator)."""
+    import bvc_b200 as bvc
+    g = jepa_case(tag)[0]
+    torch.manual_seed(seed)
+    coll = bvc.MaskCollator(input_size=(224, 224), patch_size=16, pred_mask_scale=(0.15, 0.2), enc_mask_scale=(0.85, 1.0),
+                            aspect_ratio=(0.75, 1.5), nenc=1, npred=4, allow_overlap=False, min_keep=10)
+    batch, m_enc, m_pred = coll([torch.zeros(1) for _ in range(B)])
+    assert batch.shape == (B, 1) and len(m_enc) == 1 and len(m_pred) == 4
+    m_enc = bvc.update_masks(m_enc, 224, 16, 16, 2, isencoder=True)
+    m_pred = bvc.update_masks(m_pred, 224, 16, 16, 2, isencoder=False)
+    assert torch.equal(torch.stack(list(m_enc)), torch.from_numpy(g["masks_enc"]))
+    assert torch.equal(torch.stack(list(m_pred)), torch.from_numpy(g["masks_pred"]))
+    assert int(torch.stack(list(m_pred)).min()) >= 7 * 196 and int(torch.stack(list(m_enc)).max()) < 196
+    assert coll.step() == 1   # the shared counter advanced once for the batch above

@@ -66,8 +66,8 @@ def apply_masks(x, masks):
     """mask.py:58-67: x [B, N, D], masks = list of [B, K] index tensors -> [len(masks) * B, K, D] (autograd-aware)."""
     if x.dim() != 3:
         raise ValueError("x must be [B, N, D]")
-    if x.dtype not in (torch.float32, torch.bfloat16, torch.float16):
-        raise ValueError("x must be fp32 / bf16 / fp16")
+    if x.dtype not in (torch.float32, torch.bfloat16):
+        raise ValueError("x must be fp32 or bf16 (the backward accumulates in x's dtype)")
     idx, n_masks, K = _stack_masks(masks, x.shape[0])
     return _ApplyMasksFn.apply(x.contiguous(), idx.to(x.device), n_masks, K)
 

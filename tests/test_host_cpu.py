@@ -161,6 +161,8 @@ def test_jepa_host_mirror_validates_before_touching_cuda():
     with pytest.raises(ValueError):
         bvc.apply_masks(torch.randn(10, 8), [torch.zeros(2, 3, dtype=torch.int64)])
     with pytest.raises(ValueError):
+        bvc.apply_masks(x.half(), [torch.zeros(2, 3, dtype=torch.int64)])   # fp16 is not a dtype of this path
+    with pytest.raises(ValueError):
         bvc.repeat_interleave_batch(torch.randn(5, 8), 2, 2)
     with pytest.raises(ValueError):
         bvc.smooth_l1_loss(torch.randn(4, 4), torch.randn(4, 5))

@@ -12,7 +12,7 @@ from .modeling_videomae import (  # noqa: F401
     get_sinusoid_encoding_table,
 )
 from .masking import TubeMaskingGenerator, RandomMaskingGenerator, batch_masks  # noqa: F401
-from .ddputils import AllReduce  # noqa: F401
+from .ddputils import AllReduce, AllGather  # noqa: F401
 from .optim import FusedSGD  # noqa: F401
 from .ddp import DistributedDataParallel  # noqa: F401
 from .simclr import info_nce_loss, get_special_matrix, make_masks as make_simclr_masks  # noqa: F401

@@ -33,6 +33,44 @@ def test_allreduce_mirror_world2():
     assert out[0] == (1.5, 3.0) and out[1] == (1.5, 3.0)
 
 
+def _gather_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, ROOT)
+    import bvc_b200 as bvc
+    sys.path.insert(0, "/root/reference/pretraining/predictive")
+    x = (torch.arange(6, dtype=torch.float32).reshape(3, 2) + 10 * rank).requires_grad_(True)
+    y = bvc.AllGather.apply(x)
+    w = torch.arange(12, dtype=torch.float32).reshape(6, 2) * (rank + 1)     # a different upstream gradient per rank
+    (y * w).sum().backward()
+    res = {"y": y.detach().clone(), "gx": x.grad.clone()}
+    try:  # the reference's own class, when the reference tree is present (build container)
+        import distributed as RD
+        xr = x.detach().clone().requires_grad_(True)
+        yr = RD.AllGather.apply(xr)
+        (yr * w).sum().backward()
+        res["ref_equal"] = bool(torch.equal(yr, y) and torch.equal(xr.grad, x.grad))
+    except ImportError:
+        res["ref_equal"] = None
+    out[rank] = res
+    dist.destroy_process_group()
+
+
+def test_allgather_mirror_world2():
+    """bvc_b200.AllGather (predictive/distributed.py:49-76): forward = rows of every rank in rank order; backward =
+    this rank's rows of the gradient summed over ranks -- and equal to the reference's class where that is importable."""
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_gather_worker, args=(2, 29613, out), nprocs=2, join=True)
+    base = torch.arange(6, dtype=torch.float32).reshape(3, 2)
+    want_y = torch.cat([base, base + 10])
+    w_sum = torch.arange(12, dtype=torch.float32).reshape(6, 2) * 3          # (1 + 2) x the per-rank gradient
+    for r in (0, 1):
+        assert torch.equal(out[r]["y"], want_y)
+        assert torch.equal(out[r]["gx"], w_sum[3 * r:3 * r + 3])
+        assert out[r]["ref_equal"] in (True, None)
+
+
 def test_allreduce_is_identity_without_process_group():
     sys.path.insert(0, ROOT)
     import bvc_b200 as bvc
@@ -40,6 +78,10 @@ def test_allreduce_is_identity_without_process_group():
     y = bvc.AllReduce.apply(x * 1.0)
     y.backward()
     assert float(y) == 2.0 and float(x.grad) == 1.0
+    z = torch.ones(2, 3, requires_grad=True)
+    g = bvc.AllGather.apply(z)                       # identity (values and gradient) without a process group
+    g.sum().backward()
+    assert g.shape == (2, 3) and torch.equal(z.grad, torch.ones(2, 3))
 
 
 def test_reference_arm_prints_on_rank0_only():

@@ -166,7 +166,7 @@ def ema_update(encoder_params, target_params, m):
     qs, ks = list(encoder_params), list(target_params)
     if len(qs) != len(ks) or not qs:
         raise ValueError("parameter lists must be non-empty and of equal length")
-    key = tuple((k.data_ptr(), q.data_ptr(), k.numel()) for q, k in zip(qs, ks))
+    key = tuple((k.data_ptr(), q.data_ptr(), k.numel(), k.dtype, q.dtype) for q, k in zip(qs, ks))
     hit = _ema_tables.get(key)
     if hit is None:
         for q, k in zip(qs, ks):

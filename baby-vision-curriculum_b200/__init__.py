@@ -13,7 +13,7 @@ from .modeling_videomae import (  # noqa: F401
 )
 from .masking import TubeMaskingGenerator, RandomMaskingGenerator, batch_masks  # noqa: F401
 from .ddputils import AllReduce, AllGather  # noqa: F401
-from .optim import FusedSGD  # noqa: F401
+from .optim import FusedSGD, FusedAdam, FusedAdamW  # noqa: F401
 from .ddp import DistributedDataParallel  # noqa: F401
 from .simclr import info_nce_loss, get_special_matrix, make_masks as make_simclr_masks  # noqa: F401
 from .jepa import (apply_masks, repeat_interleave_batch, jepa_targets, smooth_l1_loss, ema_update,  # noqa: F401

@@ -12,7 +12,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libbvc.so")
-ABI_VERSION = 12
+ABI_VERSION = 13
 
 _lib = None
 
@@ -38,7 +38,6 @@ class GemmArgs(C.Structure):
 
 _SIGNATURES = {
     "bvc_abi_version": (C.c_int, []),
-    "bvc_set_sm_limit": (C.c_int, [C.c_int32]),
     "bvc_mask_count": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "bvc_mask_to_index": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_void_p]),
@@ -77,6 +76,9 @@ _SIGNATURES = {
                                         C.c_float, C.c_void_p, C.c_void_p]),
     "bvc_sgd_step": (C.c_int, [C.c_void_p, C.c_int32, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int32,
                                C.c_void_p, C.c_void_p, C.c_void_p]),
+    "bvc_adam_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
+                                C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "bvc_grad_nonfinite": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "bvc_jepa_apply_masks": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32,
                                        C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "bvc_jepa_apply_masks_bwd": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
@@ -350,6 +352,23 @@ def sgd_step(table, n_entries, total_elems, lr, momentum, dampening, weight_deca
     _count()
 
 
+def adam_step(table, v_table, n_entries, total_elems, lr, beta1, beta2, eps, weight_decay, decoupled, step, grad_scale,
+              found_inf, bytes_per_elem):
+    _cuda(table, v_table, step, grad_scale, found_inf)
+    with _Timed("adam_step", 0.0, float(total_elems) * bytes_per_elem):
+        _check(load().bvc_adam_step(_p(table), _p(v_table), n_entries, lr, beta1, beta2, eps, weight_decay,
+                                    1 if decoupled else 0, _p(step), _p(grad_scale), _p(found_inf), _stream()),
+               "bvc_adam_step")
+    _count(2)
+
+
+def grad_nonfinite(table, n_entries, total_elems, found_inf):
+    _cuda(table, found_inf)
+    with _Timed("grad_nonfinite", 0.0, float(total_elems) * 4):
+        _check(load().bvc_grad_nonfinite(_p(table), n_entries, _p(found_inf), _stream()), "bvc_grad_nonfinite")
+    _count()
+
+
 def nce_normalize_split(feats, n, D, eps, a_split, b_split, bk_split, inv_norm):
     _cuda(feats, a_split, b_split, bk_split, inv_norm)
     is_bf16 = 1 if feats.dtype == torch.bfloat16 else 0
@@ -450,6 +469,3 @@ def ema_update(table, n_entries, momentum, total_elems):
     _count()
 
 
-def set_sm_limit(n_sms):
-    """Size the persistent kernels' grids for n_sms SMs (0 = all); returns the previous setting."""
-    return int(load().bvc_set_sm_limit(int(n_sms)))

@@ -17,8 +17,16 @@ LIB = os.path.join(HERE, "libbvc.so")
 OBJ_DIR = os.path.join(HERE, "build")
 SOURCES = ["gemm.cu", "gemm_bn64.cu", "gemm_bn128.cu", "gemm_bn192.cu", "gemm_bn256.cu", "gemm_pair128.cu", "gemm_pair192.cu", "gemm_pair256.cu", "rows.cu", "patchify.cu", "attn.cu", "attn_small.cu", "optim.cu", "nce.cu", "jepa.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--use_fast_math",
+FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
+# --use_fast_math only where the hot loops are exponentials on the MUFU pipe (softmax, GELU) feeding bf16 outputs: the
+# tensor-core kernels.  The fp32 statistics / optimizer / index kernels (rows, patchify, optim, nce, jepa) keep IEEE
+# division, square root and denormals.
+FAST_MATH = ("gemm", "attn")
+
+
+def _flags(src):
+    return FLAGS + (["--use_fast_math"] if os.path.basename(src).startswith(FAST_MATH) else [])
 
 
 def _digest(paths):
@@ -26,7 +34,7 @@ def _digest(paths):
     for p in sorted(paths):
         with open(p, "rb") as f:
             h.update(f.read())
-    h.update(" ".join(FLAGS).encode())
+    h.update((" ".join(FLAGS) + "|" + ",".join(FAST_MATH)).encode())
     return h.hexdigest()
 
 
@@ -43,7 +51,7 @@ def build(force=False, verbose=False):
     for s in srcs:
         o = os.path.join(OBJ_DIR, os.path.basename(s) + ".o")
         objs.append(o)
-        cmd = [NVCC] + FLAGS + ["-c", s, "-o", o]
+        cmd = [NVCC] + _flags(s) + ["-c", s, "-o", o]
         procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     log = []
     for s, p in procs:

@@ -76,14 +76,6 @@ inline int make_tmap(CUtensorMap* m, CUtensorMapDataType dt, int rank, const voi
   return BVC_OK;
 }
 
-// bvc_set_sm_limit: how many SMs the persistent kernels size their grids for (0 = all).  A data-parallel wrapper
-// lowers it while gradient all-reduces are in flight: NCCL's kernels hold a few SMs, and a persistent kernel launched
-// with one CTA per PHYSICAL SM then runs its last CTAs -- and their statically assigned share of the work -- as a
-// second wave.
-inline int& sm_limit_ref() {
-  static int limit = 0;
-  return limit;
-}
 inline int num_sms() {
   static int n = []() {
     int dev = 0, v = 0;
@@ -91,8 +83,7 @@ inline int num_sms() {
     if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) return 148;
     return v;
   }();
-  const int lim = sm_limit_ref();
-  return (lim > 0 && lim < n) ? lim : n;
+  return n;
 }
 
 }  // namespace bvc

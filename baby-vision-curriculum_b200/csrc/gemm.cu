@@ -96,12 +96,6 @@ __global__ void loss_finalize_kernel(const float* __restrict__ partials, long lo
 
 extern "C" int bvc_abi_version(void) { return BVC_ABI_VERSION; }
 
-extern "C" int bvc_set_sm_limit(int32_t n_sms) {
-  const int prev = bvc::sm_limit_ref();
-  bvc::sm_limit_ref() = n_sms > 0 ? n_sms : 0;
-  return prev;
-}
-
 static int resolve_block_n(int M, int N, int block_n, int K = 1 << 30, bool wgrad = false) {
   if (block_n == 64 || block_n == 128 || block_n == 192 || block_n == 256) return block_n;
   return bvc::pick_block_n(M, N, K, wgrad);

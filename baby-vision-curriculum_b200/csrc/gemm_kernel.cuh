@@ -758,7 +758,7 @@ static int launch_gemm(const bvc_gemm_args* a, cudaStream_t stream) {
                   a->res == nullptr && a->target == nullptr);
   }
   const long long total = (long long)p.tiles_m * p.tiles_n * p.k_splits;
-  int cap = PAIR ? num_sms() / 2 : num_sms();  // honours bvc_set_sm_limit at every launch
+  int cap = PAIR ? num_sms() / 2 : num_sms();
   if (cap > max_workers) cap = max_workers;
   const int workers = (int)(total < cap ? total : cap);
   if constexpr (PAIR != 0) {

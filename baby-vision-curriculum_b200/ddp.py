@@ -17,7 +17,6 @@ broadcast from rank 0 at construction like DDP's _sync_module_states.
 from __future__ import annotations
 
 import contextlib
-import os
 
 import torch
 import torch.distributed as dist
@@ -25,42 +24,50 @@ from torch import nn
 
 
 class GradSync:
-    """Per-model gradient synchroniser: stages call reduce(flat) from inside their backward."""
+    """Per-model gradient synchroniser: stages call reduce(flat, params, views) from inside their backward.
+
+    The mode of a backward pass is decided AT BACKWARD TIME, when the pass's first stage reports (nothing of this pass
+    has reached a .grad yet): if no parameter has a .grad, autograd will adopt the stage views as the .grad tensors
+    and every stage buffer is all-reduced in place, asynchronously, the moment it is complete ("overlapped"); if any
+    .grad exists (gradient accumulation, zero_grad(set_to_none=False), a second backward through the same model before
+    the first one's optimizer step), autograd ADDS the views into the existing tensors, so only the accumulated
+    tensors may be reduced, at the end of the pass ("deferred" -- torch DDP's semantics after no_sync()).  Deciding at
+    forward time was wrong for fwd, fwd, bwd, bwd: the second backward added local views into .grad tensors while
+    their in-place all-reduce was still running.
+    At the end of an overlapped pass every parameter's .grad is checked to alias the reduced view it was handed; a
+    .grad that autograd copied instead of adopting (tensor hooks, create_graph) is overwritten with the reduced view."""
 
     def __init__(self, process_group=None, params=()):
         self.pg = process_group
         self.world = dist.get_world_size(process_group)
         self.enabled = True
-        self.deferred = False           # set per forward: .grad tensors already exist (accumulation / set_to_none=False)
+        self.deferred = False           # mode of the current / most recent backward pass
         self._params = list(params)
         self._works = []
+        self._pairs = []                # (parameter, reduced view) of the overlapped stages of this pass
         self._armed = False
         backend = dist.get_backend(process_group)
         self._avg = backend == "nccl"   # gloo (CPU tests) has no AVG: SUM then scale
         self.launched = 0               # collectives launched (bench / tests)
-        # SMs left to NCCL while all-reduces are in flight (BVC_DDP_SM_RESERVE, default NCCL_MAX_CTAS if that is set):
-        # the persistent kernels of the rest of the backward size their grids for the remaining SMs instead of
-        # running their last CTAs, and those CTAs' share of the work, as a second wave (include/bvc.h bvc_set_sm_limit)
-        self._sm_limit = 0
-        if backend == "nccl" and torch.cuda.is_available():
-            reserve = int(os.environ.get("BVC_DDP_SM_RESERVE", os.environ.get("NCCL_MAX_CTAS", "0")) or 0)
-            n = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
-            if 0 < reserve < n // 2:
-                self._sm_limit = n - reserve
+        self.adopted = 0                # .grad tensors found aliasing their reduced stage buffer (last pass)
+        self.copied = 0                 # .grad tensors that had to be overwritten with the reduced view (last pass)
 
-    def reduce(self, flat: torch.Tensor):
+    def reduce(self, flat: torch.Tensor, params=None, views=None):
         if not self.enabled or self.world == 1:
             return
         if not self._armed:
-            # first bucket of this backward pass: have the engine call us when the pass is over
+            # first bucket of this backward pass: have the engine call us when the pass is over, and fix the mode
             torch.autograd.Variable._execution_engine.queue_callback(self._finalize)
             self._armed = True
-            if self._sm_limit:
-                from . import _lib as L
-                L.set_sm_limit(self._sm_limit)
+            self.deferred = any(p.grad is not None for p in self._params)
         if self.deferred:
-            return  # autograd will ADD this stage's gradients into existing .grad tensors: reduce those at the end
+            return  # autograd ADDS this stage's gradients into existing .grad tensors: reduce those at the end
         self._launch(flat)
+        if params is not None and views is not None:
+            # NOT the view tensors themselves: a second reference keeps autograd's AccumulateGrad from adopting them
+            # (it steals a gradient only when it holds the last reference) -- remember where they live instead
+            for p, v in zip(params, views):
+                self._pairs.append((p, v.data_ptr(), v.numel(), v.untyped_storage(), v.storage_offset()))
 
     def _launch(self, t):
         op = dist.ReduceOp.AVG if self._avg else dist.ReduceOp.SUM
@@ -68,10 +75,7 @@ class GradSync:
         self.launched += 1
 
     def begin_forward(self):
-        """Overlapped mode needs autograd to adopt the stage buffers as the .grad tensors (zero_grad(set_to_none=True),
-        the torch >= 2.0 default and what the reference's optimizer.zero_grad() does); if gradients are already
-        allocated they are accumulated into, and only the accumulated result may be reduced."""
-        self.deferred = any(p.grad is not None for p in self._params)
+        """Kept for callers of the round-1 interface: the mode is decided at backward time (see the class docstring)."""
 
     def _finalize(self):
         if self.deferred:
@@ -79,13 +83,27 @@ class GradSync:
                 if p.grad is not None:
                     self._launch(p.grad)
         works, self._works, self._armed = self._works, [], False
-        if self._sm_limit:
-            from . import _lib as L
-            L.set_sm_limit(0)
+        pairs, self._pairs = self._pairs, []
         for w, flat in works:
             w.wait()  # stream-level on CUDA: the host does not block
             if not self._avg:
                 flat.div_(self.world)
+        adopted = copied = 0
+        for p, ptr, n, storage, offset in pairs:
+            g = p.grad
+            if g is not None and g.data_ptr() == ptr and g.numel() == n:
+                adopted += 1
+            else:
+                # autograd copied the view (on the compute stream, racing the in-place collective): the reduced view is
+                # the gradient of this pass, and .grad was None when the pass began
+                with torch.no_grad():
+                    v = torch.empty(0, dtype=p.dtype, device=p.device).set_(storage, offset, p.shape)
+                    if g is None:
+                        p.grad = v.clone()
+                    else:
+                        g.copy_(v)
+                copied += 1
+        self.adopted, self.copied = adopted, copied
 
 
 class DistributedDataParallel(nn.Module):
@@ -115,8 +133,6 @@ class DistributedDataParallel(nn.Module):
                                group=process_group)
 
     def forward(self, *args, **kwargs):
-        if torch.is_grad_enabled():
-            self.sync.begin_forward()
         return self.module(*args, **kwargs)
 
     @contextlib.contextmanager

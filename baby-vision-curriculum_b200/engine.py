@@ -34,6 +34,7 @@ class Bf16Cache:
         self._plan = None       # (ptr signature, table tensor, n_entries, total elems, views)
         self._versions = None
         self._params = []
+        self.epoch = 0          # bumped whenever the copies are rewritten (refresh / optimizer shadow update)
 
     def register(self, entries, device):
         """entries: list of (name, kind, params) with kind 'w' (one weight) or 'qkv' (wq, wk, wv, qb, vb)."""
@@ -91,6 +92,7 @@ class Bf16Cache:
             _, table, n, total, _, _, _ = self._plan
             L.cast_multi(table, n, total)
             self._versions = ver
+            self.epoch += 1
 
     def shadows(self):
         """{id(param): (copy pointer, copy_is_f32)} when every copy matches its parameter right now, else {} --
@@ -103,6 +105,7 @@ class Bf16Cache:
 
     def mark_synced(self):
         self._versions = tuple(p._version for p in self._params)
+        self.epoch += 1
 
     def weight(self, name):
         return self._plan[4][name]
@@ -151,11 +154,23 @@ class StepState:
         self.B = self.N = self.nv = self.nm = 0
         self.vis_idx = self.msk_idx = self.slot = self.status = None
         self.sync = None  # ddp.GradSync when the model is wrapped in bvc_b200.DistributedDataParallel
+        self.epoch = cache.epoch  # the stages' backward uses the SAME bf16 weight copies the forward read (see check())
+        self.stage_params = {}  # stage name -> its parameters, in the order the stage's backward returns their gradients
 
-    def reduce(self, flat):
-        """A stage's parameter gradients (one contiguous buffer) are complete on the stream: start their all-reduce."""
+    def check(self):
+        """The stages keep raw references to the shared bf16 weight copies instead of save_for_backward; an optimizer
+        step / refresh between a forward and its backward rewrites them in place.  torch raises a version-counter
+        error in that situation -- so do we."""
+        if self.cache.epoch != self.epoch:
+            raise RuntimeError("one of the variables needed for gradient computation has been modified by an inplace "
+                               "operation: the model's weights (bf16 operand copies) were updated between this forward "
+                               "and its backward")
+
+    def reduce(self, flat, name=None, views=None):
+        """A stage's parameter gradients (one contiguous buffer) are complete on the stream: start their all-reduce.
+        `views` are the gradient tensors the stage returns to autograd, in the order of stage_params[name]."""
         if self.sync is not None:
-            self.sync.reduce(flat)
+            self.sync.reduce(flat, self.stage_params.get(name), views)
 
 
 def _contig_grad(g):
@@ -222,12 +237,13 @@ class EmbedFn(torch.autograd.Function):
         wb = st.cache.weight(name)
         x = _empty((M, D), F32, patches.device)
         L.gemm(patches, wb, M, D, K, out_f32=x, bias=b.detach(), res=pos, ldr=D, res_idx=st.vis_idx)
-        ctx.st, ctx.patches, ctx.dims, ctx.wshape = st, patches, (M, D, K), w.shape
+        ctx.st, ctx.patches, ctx.dims, ctx.wshape, ctx.name = st, patches, (M, D, K), w.shape, name
         return x
 
     @staticmethod
     def backward(ctx, dx):
         st, patches = ctx.st, ctx.patches
+        st.check()
         M, D, K = ctx.dims
         dx = _contig_grad(dx)
         dxb, cs = st.side.take(dx, M, D)
@@ -238,7 +254,7 @@ class EmbedFn(torch.autograd.Function):
             db = cs
         else:
             L.colsum(dxb, M, D, db)
-        st.reduce(flat)
+        st.reduce(flat, ctx.name, (dw, db))
         return dw, db, None, None, None, None
 
 
@@ -282,6 +298,7 @@ class BlockFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dxo):
         st = ctx.st
+        st.check()
         M, d, ff, B, S, H, scale = ctx.geom
         x, u1, stats, qkv, attn, lse, x_mid, u2, gp, act, ln1w, ln2w, wqkv, wob, w1b, w2b = ctx.saved
         ctx.saved = None
@@ -343,11 +360,12 @@ class BlockFn(torch.autograd.Function):
         L.layernorm_bwd(d_u1, x, stats[0], stats[1], ln1w.detach(), dxm, M, d, dx, dxb, g_ln1w, g_ln1b, dxsum=cs_in)
         st.side.put(dx, dxb, cs_in)
         wg.join()  # the weight gradients are complete on the current stream from here on
-        st.reduce(flat)
 
         gw = g_wqkv.view(3, d, d)
-        return (dx, g_ln1w, g_ln1b, gw[0], gw[1], gw[2], g_bqkv[0:d], g_bqkv[2 * d:3 * d], g_wo.view(d, d), g_bo,
-                g_ln2w, g_ln2b, g_w1.view(ff, d), g_b1, g_w2.view(d, ff), g_b2, None, None, None, None, None, None)
+        grads = (g_ln1w, g_ln1b, gw[0], gw[1], gw[2], g_bqkv[0:d], g_bqkv[2 * d:3 * d], g_wo.view(d, d), g_bo,
+                 g_ln2w, g_ln2b, g_w1.view(ff, d), g_b1, g_w2.view(d, ff), g_b2)
+        st.reduce(flat, ctx.name, grads)
+        return (dx,) + grads + (None, None, None, None, None, None)
 
 
 # ==================================================================================================== enc -> dec
@@ -367,12 +385,13 @@ class EncToDecFn(torch.autograd.Function):
         L.gemm(hb, wb, M, Dd, D, out_f32=xf, res=pos, ldr=Dd, res_idx=st.vis_idx, out_seg=nv, out_seg_stride=N,
                out_seg_off=0)
         L.decoder_mask_rows(xf, mask_token.detach().reshape(-1), pos, st.msk_idx, B, N, nv, Dd)
-        ctx.st, ctx.hb, ctx.wb, ctx.dims = st, hb, wb, (M, D, Dd)
+        ctx.st, ctx.hb, ctx.wb, ctx.dims, ctx.name = st, hb, wb, (M, D, Dd), name
         return xf
 
     @staticmethod
     def backward(ctx, dxf):
         st, hb, wb = ctx.st, ctx.hb, ctx.wb
+        st.check()
         M, D, Dd = ctx.dims
         B, N, nv, nm = st.B, st.N, st.nv, st.nm
         dev = dxf.device
@@ -388,8 +407,9 @@ class EncToDecFn(torch.autograd.Function):
         st.side.put(dh, dhb)
         L.gemm(dz, hb, Dd, D, M, a_mn=True, b_mn=True, lda=Dd, ldb=D, out_f32=g_w, k_splits=0)
         L.colsum(dxf, B * nm, Dd, g_tok, ld=Dd, seg=(nm, N, nv))
-        st.reduce(flat)
-        return dh, g_w, g_tok.view(1, 1, Dd), None, None, None
+        g_tok = g_tok.view(1, 1, Dd)
+        st.reduce(flat, ctx.name, (g_w, g_tok))
+        return dh, g_w, g_tok, None, None, None
 
 
 # ==================================================================================================== head + loss
@@ -399,7 +419,7 @@ class HeadLossFn(torch.autograd.Function):
     the backward, whose scale 2/numel * grad_output is applied inside the dgrad / wgrad / bias-sum kernels."""
 
     @staticmethod
-    def forward(ctx, xf, nw, nb, wh, bh, target, st: StepState, name, want_logits):
+    def forward(ctx, xf, nw, nb, wh, bh, target, st: StepState, name):
         dev = xf.device
         B, N, nv, nm = st.B, st.N, st.nv, st.nm
         Dd = xf.shape[1]
@@ -410,20 +430,22 @@ class HeadLossFn(torch.autograd.Function):
         stats = _empty((2, M), F32, dev)
         L.layernorm_fwd(xf, nw.detach(), nb.detach(), 1e-5, M, Dd, z, stats[0], stats[1], ldx=Dd, seg=(nm, N, nv))
         diff = _empty((M, K), BF16, dev)
-        logits = _empty((M, K), BF16, dev) if want_logits else None
         bn = 192 if K % 192 == 0 else 0  # measured best for the short-K head GEMM (profiles/r01_gemm_tune.log)
         part = _empty((L.gemm_loss_slots(M, K, bn),), F32, dev)
+        # the logits themselves are not written (277 MB per step at batch 64 that the training loop never reads): the
+        # output object re-runs the projection on z if `.logits` is accessed (modeling_videomae.py)
         L.gemm(z, whb, M, K, Dd, out_bf16=diff, bias=bh.detach(), target=target, ldt=K, loss_partial=part,
-               logits_out=logits, block_n=bn)
+               block_n=bn)
         loss = _empty((), F32, dev)
         L.loss_finalize(part, float(M) * K, st.status, loss)
-        ctx.st, ctx.saved, ctx.dims = st, (xf, stats, z, diff, nw, whb), (M, Dd, K)
-        st.logits = logits
+        ctx.st, ctx.saved, ctx.dims, ctx.name = st, (xf, stats, z, diff, nw, whb), (M, Dd, K), name
+        st.head_operands = (z, whb, bh, bn)
         return loss
 
     @staticmethod
     def backward(ctx, g):
         st = ctx.st
+        st.check()
         xf, stats, z, diff, nw, whb = ctx.saved
         ctx.saved = None
         M, Dd, K = ctx.dims
@@ -445,5 +467,5 @@ class HeadLossFn(torch.autograd.Function):
         L.layernorm_bwd(dz, xf, stats[0], stats[1], nw.detach(), None, M, Dd, dxf, dxfb, g_nw, g_nb, ldx=Dd,
                         seg=(nm, N, nv), dxsum=cs)  # visible rows are zero: colsum over the Nm rows == over all rows
         st.side.put(dxf, dxfb, cs)
-        st.reduce(flat)
-        return dxf, g_nw, g_nb, g_wh, g_bh, None, None, None, None
+        st.reduce(flat, ctx.name, (g_nw, g_nb, g_wh, g_bh))
+        return dxf, g_nw, g_nb, g_wh, g_bh, None, None, None

@@ -50,17 +50,34 @@ class VideoMAEConfig:
     norm_pix_loss: bool = True
 
 
-@dataclass
 class VideoMAEForPreTrainingOutput:
-    """HF:64-75."""
+    """HF:64-75 (`loss`, `logits`, `hidden_states`, `attentions`; tuple-style indexing over the non-None fields).
 
-    loss: Optional[torch.Tensor] = None
-    logits: Optional[torch.Tensor] = None
-    hidden_states: Optional[tuple] = None
-    attentions: Optional[tuple] = None
+    `logits` ([B, Nm, 1536] bf16, what HF's autocast forward returns) is materialised on first access: the training
+    loop (pretrain_videomae.py:301-302) reads only `.loss`, and the fused head + MSE kernel needs the logits only in
+    registers -- writing them every step cost 277 MB of HBM traffic at batch 64 that nobody read.  The first access runs
+    the head projection once more on the saved decoder output (same kernel, same tile shape, same accumulation order:
+    the values are the ones the loss was computed from); it must happen before the weights are updated."""
+
+    def __init__(self, loss=None, logits=None, hidden_states=None, attentions=None, logits_fn=None):
+        self.loss = loss
+        self._logits = logits
+        self._logits_fn = logits_fn
+        self.hidden_states = hidden_states
+        self.attentions = attentions
+
+    @property
+    def logits(self):
+        if self._logits is None and self._logits_fn is not None:
+            self._logits = self._logits_fn()
+            self._logits_fn = None
+        return self._logits
 
     def __getitem__(self, i):
         return tuple(v for v in (self.loss, self.logits, self.hidden_states, self.attentions) if v is not None)[i]
+
+    def __repr__(self):
+        return f"VideoMAEForPreTrainingOutput(loss={self.loss!r}, logits=<{'ready' if self._logits is not None else 'lazy'}>)"
 
 
 def get_sinusoid_encoding_table(n_position: int, d_hid: int) -> torch.Tensor:
@@ -194,10 +211,16 @@ class VideoMAEForPreTraining(nn.Module):
         self._pos_dev = {}
         self._cache = Bf16Cache()
         self._grad_sync = None   # set by bvc_b200.DistributedDataParallel (ddp.py)
+        self._stage_param_map = None
         self._pixel_norm = None  # (mean[3], std[3]) for uint8 pixel_values, see set_input_normalization
-        self._nv = None          # cached visible-token count (validated on device every step)
+        self._nv = None          # visible-token count of the current call
+        self._nv_cache = {}      # static_mask_count: (B, N, device) -> count read back once
         self._status = None      # device int32 flag: a mask row violated the equal-count contract
-        self._strict = os.environ.get("BVC_STRICT_MASK", "0") == "1"
+        self._status_host = self._status_event = None
+        self.mask_mismatches = 0
+        # True: trust the first call's visible-token count for later calls of the same shape (no per-call readback of
+        # a CUDA mask; validated on the device).  Default: every call counts its own mask, like HF.
+        self.static_mask_count = os.environ.get("BVC_STATIC_MASK_COUNT", "0") == "1"
         self._init_weights(c.initializer_range)
 
     # -- init: modeling_utils.py:2285-2325 (normal(0, initializer_range) weights, zero biases, LN 1/0) -------------
@@ -236,6 +259,20 @@ class VideoMAEForPreTraining(nn.Module):
         ents.append(("head", "w", (self.decoder.head.weight,)))
         return ents
 
+    def _stage_params(self):
+        """stage name -> parameters in the order that stage's backward returns their gradients (engine.py); the
+        gradient synchroniser checks each .grad against the reduced view it was handed (ddp.GradSync)."""
+        if self._stage_param_map is None:
+            proj = self.videomae.embeddings.patch_embeddings.projection
+            m = {"pe": (proj.weight, proj.bias), "e2d": (self.encoder_to_decoder.weight, self.mask_token),
+                 "head": (self.decoder.norm.weight, self.decoder.norm.bias, self.decoder.head.weight,
+                          self.decoder.head.bias)}
+            for tag, layers in (("e", self.videomae.encoder.layer), ("d", self.decoder.decoder_layers)):
+                for i, layer in enumerate(layers):
+                    m[f"{tag}{i}."] = layer.flat_params()
+            self._stage_param_map = m
+        return self._stage_param_map
+
     def set_input_normalization(self, mean, std):
         """Accept uint8 clips: `model(pixel_values_uint8, ...)` then applies the dataset's ToTensor + Normalize
         (pretraining/generative/homeview.py:218-231, `Normalize(mean, std)` after `/ 255`) inside the patchify kernel --
@@ -253,6 +290,42 @@ class VideoMAEForPreTraining(nn.Module):
 
     def weight_shadows_synced(self):
         self._cache.mark_synced()
+
+    def _visible_count(self, mask_in, m_dev, B, N, dev):
+        """Visible tokens per row (HF:121-122 reshapes `embeddings[~mask]` to [B, -1, C]: every row must mask the same
+        number of tokens, and any such number is legal on any call).  A mask that still lives on the HOST -- where the
+        reference builds it, pretrain_videomae.py:293-297 -- is counted there: exact, no device round trip.  A CUDA mask
+        is counted on the device and read back (one small synchronising copy per call; the reference's own
+        `bool_masked_pos.to(rank)` from pageable memory synchronises the stream as well).  `static_mask_count = True`
+        opts out: the count is read back once per (batch, tokens) shape, later calls are validated on the device only
+        (mismatch -> NaN loss for that call, detected and recovered from on the next call, surfaced by
+        check_mask_status())."""
+        if not mask_in.is_cuda:
+            mh = mask_in if mask_in.dtype == torch.bool else mask_in != 0
+            cnt = (~mh).sum(dim=1)
+            if not bool((cnt == cnt[0]).all()):
+                raise ValueError("bool_masked_pos: every row must mask the same number of tokens (HF:121-122 reshape)")
+            return int(cnt[0])
+        key = (B, N, str(dev))
+        if self.static_mask_count:
+            if self._status_event is not None and self._status_event.query() and int(self._status_host[0]) != 0:
+                # an earlier call's rows did not match the cached count: forget it and count this mask for real
+                self._status.zero_()
+                self._status_host.zero_()
+                self._nv_cache.clear()
+                self.mask_mismatches += 1
+            nv = self._nv_cache.get(key)
+            if nv is not None:
+                return nv
+        cnt = torch.empty(B, dtype=torch.int32, device=dev)
+        L.mask_count(m_dev, cnt)
+        cnt = cnt.cpu()
+        if not bool((cnt == cnt[0]).all()):
+            raise ValueError("bool_masked_pos: every row must mask the same number of tokens (HF:121-122 reshape)")
+        nv = int(cnt[0])
+        if self.static_mask_count:
+            self._nv_cache[key] = nv
+        return nv
 
     def check_mask_status(self):
         """Synchronise and raise if any forward since the last check saw rows with unequal mask counts."""
@@ -288,21 +361,15 @@ class VideoMAEForPreTraining(nn.Module):
             x = x.contiguous()
         elif x.dtype != F32 or not x.is_contiguous():
             x = x.to(F32).contiguous()
-        m = bool_masked_pos.to(device=dev)
+        m = bool_masked_pos.to(device=dev, non_blocking=True)
         m = (m if m.dtype == torch.bool else m != 0).contiguous().view(torch.uint8)
 
         with torch.cuda.device(dev):
             if self._status is None or self._status.device != dev:
                 self._status = torch.zeros(1, dtype=torch.int32, device=dev)
-            # visible-token count: read back once (or every step with BVC_STRICT_MASK=1), validated on device always
-            if self._nv is None or self._strict:
-                cnt = torch.empty(B, dtype=torch.int32, device=dev)
-                L.mask_count(m, cnt)
-                cnt = cnt.cpu()
-                if not bool((cnt == cnt[0]).all()):
-                    raise ValueError("bool_masked_pos: every row must mask the same number of tokens "
-                                     "(HF:121-122 reshape)")
-                self._nv = int(cnt[0])
+                self._status_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+                self._status_event = None
+            self._nv = self._visible_count(bool_masked_pos, m, B, N, dev)
             nv = self._nv
             nm = N - nv
             if nv == 0 or nm == 0:
@@ -311,10 +378,16 @@ class VideoMAEForPreTraining(nn.Module):
             st = StepState(self._cache)
             st.B, st.N, st.nv, st.nm, st.status = B, N, nv, nm, self._status
             st.sync = self._grad_sync
+            if st.sync is not None:
+                st.stage_params = self._stage_params()
             st.vis_idx = torch.zeros((B, nv), dtype=torch.int32, device=dev)
             st.msk_idx = torch.zeros((B, nm), dtype=torch.int32, device=dev)
             st.slot = torch.empty((B, N), dtype=torch.int32, device=dev)
             L.mask_to_index(m, nv, st.vis_idx, st.msk_idx, st.slot, st.status)
+            if self.static_mask_count:
+                self._status_host.copy_(self._status, non_blocking=True)
+                self._status_event = torch.cuda.Event()
+                self._status_event.record()
 
             K = C * c.tubelet_size * c.patch_size ** 2
             patches = torch.empty((B * nv, K), dtype=BF16, device=dev)
@@ -327,6 +400,7 @@ class VideoMAEForPreTraining(nn.Module):
             proj = self.videomae.embeddings.patch_embeddings.projection
             self._cache.register(self._weight_entries(), dev)
             self._cache.refresh()
+            st.epoch = self._cache.epoch
             h = EmbedFn.apply(proj.weight, proj.bias, patches, pos_e, st, "pe")
             for i, layer in enumerate(self.videomae.encoder.layer):
                 h = BlockFn.apply(h, *layer.flat_params(), st, f"e{i}.", B, nv, c.num_attention_heads,
@@ -336,7 +410,16 @@ class VideoMAEForPreTraining(nn.Module):
                 xf = BlockFn.apply(xf, *layer.flat_params(), st, f"d{j}.", B, N, c.decoder_num_attention_heads,
                                    float(c.layer_norm_eps))
             loss = HeadLossFn.apply(xf, self.decoder.norm.weight, self.decoder.norm.bias, self.decoder.head.weight,
-                                    self.decoder.head.bias, target, st, "head", self.output_logits)
-            logits = st.logits.view(B, nm, K) if st.logits is not None else None
-            st.logits = None
-        return VideoMAEForPreTrainingOutput(loss=loss, logits=logits)
+                                    self.decoder.head.bias, target, st, "head")
+            logits_fn = None
+            if self.output_logits:
+                z, whb, bh, bn = st.head_operands
+                st.head_operands = None
+
+                def logits_fn(z=z, whb=whb, bh=bh.detach(), bn=bn, st=st, shape=(B, nm, K), dev=dev):
+                    st.check()  # the bf16 weight copies must still be the ones this forward used
+                    with torch.cuda.device(dev):
+                        out = torch.empty((shape[0] * shape[1], shape[2]), dtype=BF16, device=dev)
+                        L.gemm(z, whb, out.shape[0], shape[2], z.shape[1], out_bf16=out, bias=bh, block_n=bn)
+                    return out.view(shape)
+        return VideoMAEForPreTrainingOutput(loss=loss, logits_fn=logits_fn)

@@ -28,14 +28,10 @@ extern "C" {
 #define BVC_ERR_ARG (-1)
 #define BVC_ERR_DRIVER (-2)
 #define BVC_ERR_LAUNCH (-3)
-#define BVC_ABI_VERSION 12
+#define BVC_ABI_VERSION 13
 
 /* library / build info: returns BVC_ABI_VERSION (bumped when a signature changes) */
 int bvc_abi_version(void);
-/* Size the persistent kernels' grids for n_sms SMs instead of all of them (0 = all); returns the previous setting.
- * Host-side state, read at every launch.  bvc_b200.DistributedDataParallel lowers it by the number of CTAs NCCL may
- * hold (NCCL_MAX_CTAS) while the gradient all-reduces of a backward pass are in flight. */
-int bvc_set_sm_limit(int32_t n_sms);
 
 /* ------------------------------------------------------------------------------------------------------
  * Tube-mask indexing.  Replaces the boolean-index ops `x[~bool_masked_pos]` / `x[bool_masked_pos]`
@@ -206,6 +202,23 @@ int bvc_attn_bwd(const void* qkv, const void* out, const void* dout, const float
 int bvc_sgd_step(const void* table, int32_t n_entries, float lr, float momentum, float dampening,
                  float weight_decay, int32_t nesterov, const float* grad_scale, const float* found_inf,
                  void* stream);
+
+/* torch.optim.AdamW / Adam (pretrain_videomae.py:190-193: AdamW, betas (0.9, 0.95)) in one multi-tensor pass over
+ * the same table (m = exp_avg; m_uninit: both state buffers count as zero); exp_avg_sq_table is a device array of
+ * n_entries float* (exp_avg_sq of each entry).  Op order of torch/optim/adam.py _single_tensor_adam:
+ *   AdamW (decoupled != 0): p *= 1 - lr wd      Adam: g' += wd p
+ *   m = m + (1 - beta1)(g' - m);  v = beta2 v + (1 - beta2) g' g';   t = *step + 1
+ *   p -= lr / (1 - beta1^t) * m / (sqrt(v) / sqrt(1 - beta2^t) + eps)
+ * `step` is a device float (the group's step count before this call); a second one-thread kernel adds 1 to it after
+ * the update unless *found_inf != 0, in which case the whole call is a no-op.  g, shadow, grad_scale as bvc_sgd_step. */
+int bvc_adam_step(const void* table, const void* exp_avg_sq_table, int32_t n_entries, float lr, float beta1,
+                  float beta2, float eps, float weight_decay, int32_t decoupled, float* step,
+                  const float* grad_scale, const float* found_inf, void* stream);
+
+/* GradScaler's inf / nan check (torch._amp_foreach_non_finite_check_and_unscale_ with inv_scale 1, which re-writes
+ * every gradient) as one read-only multi-tensor launch over the g pointers of the same table:
+ * *found_inf = any non-finite gradient element ? 1 : 0. */
+int bvc_grad_nonfinite(const void* table, int32_t n_entries, float* found_inf, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------
  * SimCLR loss of the contrastive path (pretraining/contrastive/pretrain_simclr.py:114-128 info_nce_loss with the

@@ -108,7 +108,7 @@ class _StageFn(torch.autograd.Function):
         gw.add_(ctx.x * g)
         gb.add_(g)
         if ctx.owner._grad_sync is not None:
-            ctx.owner._grad_sync.reduce(flat)
+            ctx.owner._grad_sync.reduce(flat, (ctx.owner.w, ctx.owner.b), (gw, gb))
         return None, gw, gb, None
 
 
@@ -149,6 +149,24 @@ def _ddp_worker(rank, world, port, out):
     res["gw_local"] = m.w.grad.tolist()
     ddp(x).backward()  # accumulated (local + new) gets averaged, like torch DDP after no_sync
     res["gw_after_nosync"] = m.w.grad.tolist()
+    # fwd, fwd, bwd, bwd: the mode is decided at BACKWARD time -- the first backward finds no .grad and
+    # all-reduces its stage buffer in place (adopted as .grad), the second finds the .grad of the first and must
+    # accumulate locally and reduce the accumulated tensors at the end (never add into a buffer that is being reduced)
+    m.zero_grad(set_to_none=True)
+    x2 = x + 100.0
+    l1, l2 = ddp(x) * 2.0, ddp(x2) * 2.0
+    l1.backward()
+    res["adopted_1"], res["copied_1"], res["deferred_1"] = ddp.sync.adopted, ddp.sync.copied, ddp.sync.deferred
+    l2.backward()
+    res["deferred_2"] = ddp.sync.deferred
+    res["gw_ffbb"], res["gb_ffbb"] = m.w.grad.tolist(), m.b.grad.tolist()
+    # a tensor hook makes autograd hand AccumulateGrad a different tensor than the reduced view: the synchroniser
+    # must notice that .grad does not alias its stage buffer and overwrite it with the reduced values
+    m.zero_grad(set_to_none=True)
+    h = m.w.register_hook(lambda g: g * 1.0)
+    (ddp(x) * 2.0).backward()
+    h.remove()
+    res["gw_hook"], res["copied_hook"] = m.w.grad.tolist(), ddp.sync.copied
     out[rank] = res
     dist.destroy_process_group()
 
@@ -168,6 +186,10 @@ def test_bvc_ddp_world2_gloo():
         assert o["gw2"] == [2 * v for v in mean_gw]
         assert o["gw_local"] == (x0 if r == 0 else x1).tolist()
         assert o["gw_after_nosync"] == ((x0 + x1) / 2 * 2).tolist()
+        assert (o["adopted_1"], o["copied_1"], o["deferred_1"], o["deferred_2"]) == (2, 0, False, True)
+        # both ranks: mean over ranks of (2 x) + mean over ranks of (2 (x + 100)) -- torch DDP's result for this order
+        assert o["gw_ffbb"] == ((x0 + x1) / 2 * 2.0 + (x0 + x1 + 200) / 2 * 2.0).tolist() and o["gb_ffbb"] == [4.0, 4.0]
+        assert o["gw_hook"] == mean_gw and o["copied_hook"] >= 1
 
 
 def test_bvc_ddp_rejects_foreign_modules_and_unused_params():

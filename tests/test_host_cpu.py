@@ -31,9 +31,6 @@ def test_library_exports_every_declared_symbol(bvc):
     assert lib.bvc_abi_version() == bvc._lib.ABI_VERSION
     # host-only entry point: tile bookkeeping of the fused loss epilogue
     assert lib.bvc_gemm_loss_slots(256, 512, 256) == 2 * 2 * 8
-    # host-only state: the SM budget of the persistent kernels (returns the previous setting; 0 = all SMs)
-    assert bvc._lib.set_sm_limit(140) == 0 and bvc._lib.set_sm_limit(0) == 140 and bvc._lib.set_sm_limit(-3) == 0
-    assert bvc._lib.set_sm_limit(0) == 0
     assert lib.bvc_smooth_l1_slots(1) == 1 and lib.bvc_smooth_l1_slots(10 ** 9) > 1
 
 

@@ -18,3 +18,4 @@ from .ddp import DistributedDataParallel  # noqa: F401
 from .simclr import info_nce_loss, get_special_matrix, make_masks as make_simclr_masks  # noqa: F401
 from .jepa import (apply_masks, repeat_interleave_batch, jepa_targets, smooth_l1_loss, ema_update,  # noqa: F401
                    MaskCollator, update_masks)
+from . import jepa_vit  # noqa: F401,E402  (Block / convert_blocks: the predictive path's ViT block on these kernels)

@@ -38,18 +38,6 @@ __device__ long long g_trace[kTraceRoles * kTraceTiles * kTracePoints];
   } while (0)
 #endif
 
-// of every 8 consecutive column pairs, this many take the polynomial exp2 (exp2_poly2: FMA / ALU pipes) instead of
-// MUFU.EX2.  MEASURED NEGATIVE on B200 at these tile shapes (tools/gpu_attn_trace.py, B16 S1568 H6, us per pass):
-//   share   0/8     2/8     3/8     4/8
-//   KV pass 167.1   172.8   181.5   189.8
-//   Q pass  145.7   139.4   147.5   153.7       forward (B64): 438 -> 533 at 3/8
-// the ~5 extra issue slots per element cost what the freed MUFU slots save (2 compute warps per scheduler, issue- and
-// FMA-pipe-bound once the MUFU share drops), so the default is 0; kept for the next restructuring of the softmax warps.
-#ifndef BVC_POLY_NUM
-#define BVC_POLY_NUM 0
-#endif
-constexpr int kPolyNum = BVC_POLY_NUM;
-
 // ================================================================================================ forward
 // PERSISTENT, two query tiles in flight per CTA (one CTA per SM walks (query-tile PAIR, head, clip) work items):
 //   warpgroup 0: warp 0 TMA loads (the pair's two Q tiles, double-buffered across items; K/V ring shared by both
@@ -794,7 +782,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
             // P = exp2((S - lse/scale) * scale * log2e);  dS = P * (dP - delta) * scale
             const uint64_t x2 = MODE_KV ? fmul2(s2, cl2) : ffma2(s2, cl2, nl2);
             const uint64_t y2 = MODE_KV ? fmul2(p2, sc2) : ffma2(p2, sc2, nd2);
-            const uint64_t e2 = ((j >> 1) & 7) < kPolyNum ? exp2_poly2(x2) : exp2_mufu2(x2);
+            const uint64_t e2 = exp2_mufu2(x2);
             float p0, p1, d0, d1;
             unpack2(e2, p0, p1);
             unpack2(fmul2(e2, y2), d0, d1);
@@ -883,12 +871,8 @@ extern "C" int bvc_attn_fwd(const void* qkv, int32_t B, int32_t S, int32_t H, fl
   BVC_CHECK_ARG((((uintptr_t)qkv) & 15) == 0 && (((uintptr_t)out) & 15) == 0);
   // short sequences (the encoder's 160 visible tokens): whole-sequence-resident kernel, attn_small.cu
   if (S <= 192 && small_path_enabled()) return attn_small_fwd_launch(qkv, B, S, H, scale, out, lse, (cudaStream_t)stream);
-  static bool attr_done = false;
-  if (!attr_done) {
-    if (cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmem) != cudaSuccess)
-      return BVC_ERR_LAUNCH;
-    attr_done = true;
-  }
+  static const bool attr_ok = !(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmem) != cudaSuccess);  // once, thread-safe (C++11 static initialisation)
+  if (!attr_ok) return BVC_ERR_LAUNCH;
   CUtensorMap tm, to;
   int rc = make_head_tmap(&tm, qkv, 3 * H, S, B);
   if (rc) return rc;
@@ -907,13 +891,9 @@ extern "C" int bvc_attn_bwd(const void* qkv, const void* out, const void* dout, 
                             int32_t H, float scale, float* delta, void* dqkv, void* stream) {
   BVC_CHECK_ARG(qkv && out && dout && lse && delta && dqkv && B > 0 && S > 0 && H > 0);
   BVC_CHECK_ARG((((uintptr_t)qkv) & 15) == 0 && (((uintptr_t)dout) & 15) == 0 && (((uintptr_t)dqkv) & 15) == 0);
-  static bool attr_done = false;
-  if (!attr_done) {
-    if (cudaFuncSetAttribute(attn_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem) != cudaSuccess ||
-        cudaFuncSetAttribute(attn_bwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem) != cudaSuccess)
-      return BVC_ERR_LAUNCH;
-    attr_done = true;
-  }
+  static const bool attr_ok = !(cudaFuncSetAttribute(attn_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem) != cudaSuccess ||
+        cudaFuncSetAttribute(attn_bwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem) != cudaSuccess);  // once, thread-safe (C++11 static initialisation)
+  if (!attr_ok) return BVC_ERR_LAUNCH;
   cudaStream_t st = (cudaStream_t)stream;
   const long long rows = (long long)B * S * H;
   long long g = (rows + 63) / 64;

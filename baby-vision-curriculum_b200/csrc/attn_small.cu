@@ -594,12 +594,8 @@ attn_small_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_c
 
 int attn_small_bwd_launch(const void* qkv, const void* dout, const float* lse, const float* delta, int B, int S, int H,
                           float scale, void* dqkv, cudaStream_t st) {
-  static bool attr_done = false;
-  if (!attr_done) {
-    if (cudaFuncSetAttribute(attn_small_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSbSmem) != cudaSuccess)
-      return BVC_ERR_LAUNCH;
-    attr_done = true;
-  }
+  static const bool attr_ok = !(cudaFuncSetAttribute(attn_small_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSbSmem) != cudaSuccess);  // once, thread-safe (C++11 static initialisation)
+  if (!attr_ok) return BVC_ERR_LAUNCH;
   BVC_CHECK_ARG(S <= kSbMaxS);
   CUtensorMap tq, tq32, td, td32, tdq;
   if (make_head_tmap(&tq, qkv, 3 * H, S, B) || make_head_tmap(&tq32, qkv, 3 * H, S, B, 32) ||
@@ -615,12 +611,8 @@ int attn_small_bwd_launch(const void* qkv, const void* dout, const float* lse, c
 }
 
 int attn_small_fwd_launch(const void* qkv, int B, int S, int H, float scale, void* out, float* lse, cudaStream_t st) {
-  static bool attr_done = false;
-  if (!attr_done) {
-    if (cudaFuncSetAttribute(attn_small_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmSmem) != cudaSuccess)
-      return BVC_ERR_LAUNCH;
-    attr_done = true;
-  }
+  static const bool attr_ok = !(cudaFuncSetAttribute(attn_small_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmSmem) != cudaSuccess);  // once, thread-safe (C++11 static initialisation)
+  if (!attr_ok) return BVC_ERR_LAUNCH;
   CUtensorMap tm, to;
   int rc = make_head_tmap(&tm, qkv, 3 * H, S, B);
   if (rc) return rc;

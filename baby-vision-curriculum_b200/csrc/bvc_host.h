@@ -6,6 +6,10 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <mutex>
 
 #define BVC_OK 0
 #define BVC_ERR_ARG (-1)      /* bad argument (shape / alignment / null pointer) */
@@ -49,8 +53,66 @@ inline EncodeTiledFn encode_fn() {
 }
 
 // rank-N tiled tensor map. dims/box innermost first; strides_bytes has rank-1 entries (dims 1..rank-1).
+// Descriptors are CACHED per (base pointer, shape, strides, box, dtype, swizzle): a training step re-launches the same
+// ~700 kernels on buffers the caching allocator hands back at the same addresses, so after the first step every
+// descriptor of a launch is a table hit (a 128-byte copy) instead of a driver call.  A descriptor
+// depends on the address and geometry only, never on the memory's contents, so a hit can not be stale.  Thread-safe:
+// the forward and the autograd thread both launch.
+struct TmapKey {
+  const void* base;
+  uint64_t dims[5];
+  uint64_t strides[4];
+  uint32_t box[5];
+  int32_t rank, dt, sw;
+};
+struct TmapSlot {
+  TmapKey key;
+  CUtensorMap map;
+  int valid;
+};
+constexpr int kTmapSlots = 4096;  // direct-mapped
+inline std::mutex& tmap_mutex() {
+  static std::mutex mu;
+  return mu;
+}
+inline TmapSlot* tmap_table() {
+  static TmapSlot* t = static_cast<TmapSlot*>(calloc(kTmapSlots, sizeof(TmapSlot)));
+  return t;
+}
+inline unsigned long long& tmap_hits() {
+  static unsigned long long h = 0;
+  return h;
+}
+inline unsigned long long& tmap_misses() {
+  static unsigned long long m = 0;
+  return m;
+}
+
 inline int make_tmap(CUtensorMap* m, CUtensorMapDataType dt, int rank, const void* base, const uint64_t* dims,
                      const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle sw) {
+  TmapKey key;
+  memset(&key, 0, sizeof(key));
+  key.base = base;
+  key.rank = rank;
+  key.dt = (int32_t)dt;
+  key.sw = (int32_t)sw;
+  for (int i = 0; i < rank; ++i) {
+    key.dims[i] = dims[i];
+    key.box[i] = box[i];
+  }
+  for (int i = 0; i + 1 < rank; ++i) key.strides[i] = strides_bytes[i];
+  uint64_t h = 1469598103934665603ull;  // FNV-1a over the key's words
+  const uint64_t* w = reinterpret_cast<const uint64_t*>(&key);
+  for (size_t i = 0; i < sizeof(key) / 8; ++i) h = (h ^ w[i]) * 1099511628211ull;
+  TmapSlot* slot = tmap_table() + (size_t)((h ^ (h >> 29)) % kTmapSlots);
+  {
+    std::lock_guard<std::mutex> lk(tmap_mutex());
+    if (slot->valid && memcmp(&slot->key, &key, sizeof(key)) == 0) {
+      memcpy(m, &slot->map, sizeof(CUtensorMap));
+      ++tmap_hits();
+      return BVC_OK;
+    }
+  }
   EncodeTiledFn fn = encode_fn();
   if (!fn) {
     fprintf(stderr, "bvc: cuTensorMapEncodeTiled entry point unavailable\n");
@@ -72,6 +134,13 @@ inline int make_tmap(CUtensorMap* m, CUtensorMapDataType dt, int rank, const voi
             rank, (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0),
             (unsigned long long)(rank > 2 ? dims[2] : 0), box[0], rank > 1 ? box[1] : 0, rank > 2 ? box[2] : 0);
     return BVC_ERR_DRIVER;
+  }
+  {
+    std::lock_guard<std::mutex> lk(tmap_mutex());
+    slot->key = key;
+    memcpy(&slot->map, m, sizeof(CUtensorMap));
+    slot->valid = 1;
+    ++tmap_misses();
   }
   return BVC_OK;
 }

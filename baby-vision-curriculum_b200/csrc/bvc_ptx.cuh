@@ -94,24 +94,6 @@ __device__ __forceinline__ uint64_t fmul2(uint64_t a, uint64_t b) {
   asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
   return d;
 }
-// 2^x for a pair on the FMA / ALU pipes instead of the MUFU: x = n + f with n = round(x) (magic-number rounding) and
-// f in [-0.5, 0.5], 2^f by a degree-3 minimax polynomial (relative error <= 7.5e-5, mean bias 5e-6 -- two orders below
-// the bf16 rounding of the probabilities it produces), 2^n by adding n to the exponent field.  The attention kernels
-// are MUFU-bound at head_dim 64 (16 exp2 per clk per SM against 128x128 scores per tile); they send a fixed share of
-// the pairs through this path.  Inputs are clamped at -126 (the result flushes towards 2^-126 instead of wrapping).
-__device__ __forceinline__ uint64_t exp2_poly2(uint64_t x2) {
-  float x0, x1;
-  unpack2(x2, x0, x1);
-  const uint64_t xc = pack2(fmaxf(x0, -126.f), fmaxf(x1, -126.f));
-  const uint64_t t = fadd2(xc, pack2(12582912.f, 12582912.f));     // 1.5 * 2^23: the low mantissa bits hold round(x)
-  const uint64_t n = fadd2(t, pack2(-12582912.f, -12582912.f));
-  const uint64_t f = ffma2(n, pack2(-1.f, -1.f), xc);
-  uint64_t p = ffma2(pack2(0.05517161637544632f, 0.05517161637544632f), f, pack2(0.2426111251115799f, 0.2426111251115799f));
-  p = ffma2(p, f, pack2(0.6932609677314758f, 0.6932609677314758f));
-  p = ffma2(p, f, pack2(0.9999280571937561f, 0.9999280571937561f));
-  const uint32_t lo = (uint32_t)p + ((uint32_t)t << 23), hi = (uint32_t)(p >> 32) + ((uint32_t)(t >> 32) << 23);
-  return ((uint64_t)hi << 32) | lo;
-}
 __device__ __forceinline__ uint64_t exp2_mufu2(uint64_t x2) {
   float x0, x1;
   unpack2(x2, x0, x1);

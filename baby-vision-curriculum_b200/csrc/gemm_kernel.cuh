@@ -670,16 +670,16 @@ template <int BN, int A_MN, int B_MN, int EPI, int PAIR = 0>
 static int launch_gemm(const bvc_gemm_args* a, cudaStream_t stream) {
   using Cfg = GemmCfg<BN, PAIR>;
   static_assert(Cfg::kSmemBytes <= 232448, "stage ring does not fit the 227 KB of shared memory");
-  static bool attr_done = false;
-  static int max_workers = 0;  // co-resident CTAs (pair mode: clusters)
-  if (!attr_done) {
+  // once per instantiation, thread-safe (C++11 static initialisation): the forward thread and autograd's backward
+  // thread both launch
+  static const int max_workers = []() -> int {  // co-resident CTAs (pair mode: clusters); 0 = setup failed
     cudaError_t e = cudaFuncSetAttribute(gemm_kernel<BN, A_MN, B_MN, EPI, PAIR>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     if (e != cudaSuccess) {
       fprintf(stderr, "bvc: cudaFuncSetAttribute(gemm) failed: %s\n", cudaGetErrorString(e));
-      return BVC_ERR_LAUNCH;
+      return 0;
     }
-    max_workers = PAIR ? num_sms() / 2 : num_sms();
+    int mw = PAIR ? num_sms() / 2 : num_sms();
     if (PAIR) {
       // how many CTA pairs the device can hold at once (GPCs with an odd number of usable SMs lose one)
       cudaLaunchConfig_t qc = {};
@@ -695,12 +695,13 @@ static int launch_gemm(const bvc_gemm_args* a, cudaStream_t stream) {
       qc.numAttrs = 1;
       int n_clusters = 0;
       if (cudaOccupancyMaxActiveClusters(&n_clusters, gemm_kernel<BN, A_MN, B_MN, EPI, PAIR>, &qc) == cudaSuccess &&
-          n_clusters > 0 && n_clusters < max_workers)
-        max_workers = n_clusters;
+          n_clusters > 0 && n_clusters < mw)
+        mw = n_clusters;
       (void)cudaGetLastError();
     }
-    attr_done = true;
-  }
+    return mw;
+  }();
+  if (max_workers <= 0) return BVC_ERR_LAUNCH;
   CUtensorMap ta, tb;
   {
     uint64_t dims[2], strides[1];

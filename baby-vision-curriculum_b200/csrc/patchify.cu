@@ -264,19 +264,15 @@ static int patchify_launch(const void* pixels, bool u8, PixelNorm pn, const int3
   BVC_CHECK_ARG(n_items_ll < (1ll << 31));
   const int n_items = (int)n_items_ll;
   const int grid = n_items < num_sms() ? n_items : num_sms();  // persistent: one CTA per SM
-  static bool attr_done = false;
-  if (!attr_done) {
-    if (cudaFuncSetAttribute(patchify_target_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024) !=
+  static const bool attr_ok = !(cudaFuncSetAttribute(patchify_target_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024) !=
             cudaSuccess ||
         cudaFuncSetAttribute(patchify_target_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024) !=
             cudaSuccess ||
         cudaFuncSetAttribute(patchify_target_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024) !=
             cudaSuccess ||
         cudaFuncSetAttribute(patchify_target_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024) !=
-            cudaSuccess)
-      return BVC_ERR_LAUNCH;
-    attr_done = true;
-  }
+            cudaSuccess);  // once, thread-safe (C++11 static initialisation)
+  if (!attr_ok) return BVC_ERR_LAUNCH;
 #define BVC_PATCHIFY_LAUNCH(TS_, U8_)                                                                                  \
   patchify_target_kernel<TS_, U8_><<<grid, kPatchThreads, smem, st>>>(tm, slot, Tg, Hg, Wg, split, n_items, n_stages, \
                                                                       nv, N, (bf16*)patches_vis, target, norm_pix, pn)

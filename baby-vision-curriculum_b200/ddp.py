@@ -67,6 +67,8 @@ class GradSync:
             # NOT the view tensors themselves: a second reference keeps autograd's AccumulateGrad from adopting them
             # (it steals a gradient only when it holds the last reference) -- remember where they live instead
             for p, v in zip(params, views):
+                if v is None:
+                    continue
                 self._pairs.append((p, v.data_ptr(), v.numel(), v.untyped_storage(), v.storage_offset()))
 
     def _launch(self, t):

@@ -259,112 +259,153 @@ class EmbedFn(torch.autograd.Function):
 
 
 # ==================================================================================================== block
+def _block_fwd(ctx, x, ln1w, ln1b, wqkv, bqkv, wob, bo, ln2w, ln2b, w1b, b1, w2b, b2, st, name, B, S, H, eps):
+    """One pre-LN transformer block on bf16 operand copies wqkv [3d, d] / wob / w1b / w2b and fp32 biases:
+    x + Wo.Attn(LN1(x)) then + W2.gelu(W1.LN2(.)).  Shared by the HF-layout block (separate q / k / v weights, no k
+    bias: BlockFn) and the fused-qkv block of the predictive path (FusedQkvBlockFn)."""
+    dev = x.device
+    M, d = x.shape
+    ff = w1b.numel() // d
+    scale = float((d // H) ** -0.5)
+
+    u1 = _empty((M, d), BF16, dev)
+    stats = _empty((4, M), F32, dev)
+    L.layernorm_fwd(x, ln1w.detach(), ln1b.detach(), eps, M, d, u1, stats[0], stats[1])
+    qkv = _empty((M, 3 * d), BF16, dev)
+    L.gemm(u1, wqkv, M, 3 * d, d, out_bf16=qkv, bias=bqkv)
+    attn = _empty((M, d), BF16, dev)
+    lse = _empty((B, H, S), F32, dev)
+    L.attn_fwd(qkv, B, S, H, scale, attn, lse)
+    x_mid = _empty((M, d), F32, dev)
+    L.gemm(attn, wob, M, d, d, out_f32=x_mid, bias=bo.detach(), res=x, ldr=d)
+    u2 = _empty((M, d), BF16, dev)
+    L.layernorm_fwd(x_mid, ln2w.detach(), ln2b.detach(), eps, M, d, u2, stats[2], stats[3])
+    gp = _empty((M, ff), BF16, dev)   # gelu'(pre-activation): all the backward needs of it
+    act = _empty((M, ff), BF16, dev)
+    L.gemm(u2, w1b, M, ff, d, out_bf16=act, bias=b1.detach(), act=1, aux_out=gp, ld_aux=ff)
+    x_out = _empty((M, d), F32, dev)
+    L.gemm(act, w2b, M, d, ff, out_f32=x_out, bias=b2.detach(), res=x_mid, ldr=d)
+
+    ctx.st, ctx.name, ctx.geom = st, name, (M, d, ff, B, S, H, scale)
+    ctx.saved = (x, u1, stats, qkv, attn, lse, x_mid, u2, gp, act, ln1w, ln2w, wqkv, wob, w1b, w2b)
+    return x_out
+
+
+def _block_bwd(ctx, dxo):
+    """-> dx, flat gradient buffer, (g_ln1w, g_ln1b, g_wqkv [3 d d], g_bqkv [3 d], g_wo [d d], g_bo, g_ln2w, g_ln2b,
+    g_w1 [ff d], g_b1, g_w2 [d ff], g_b2): views of `flat` (g_b2 may live in the downstream stage's buffer)."""
+    st = ctx.st
+    st.check()
+    M, d, ff, B, S, H, scale = ctx.geom
+    x, u1, stats, qkv, attn, lse, x_mid, u2, gp, act, ln1w, ln2w, wqkv, wob, w1b, w2b = ctx.saved
+    ctx.saved = None
+    dev = dxo.device
+    dxo = _contig_grad(dxo)
+    dxob, cs_out = st.side.take(dxo, M, d)
+    wg = _SideStream(dev) if _WGRAD_STREAM else _NoSideStream()  # operands stay referenced until wg.join() below
+
+    # every atomically-accumulated output of this block in one zero-filled buffer (one memset); the last slot
+    # collects colsum(dx) of this block's input gradient for the stage upstream
+    sizes = [d, d, 3 * d * d, 3 * d, d * d, d, d, d, ff * d, ff, d * ff, d, d]
+    flat = torch.zeros(sum(sizes), dtype=F32, device=dev)
+    views, o = [], 0
+    for s_ in sizes:
+        views.append(flat[o:o + s_])
+        o += s_
+    g_ln1w, g_ln1b, g_wqkv, g_bqkv, g_wo, g_bo, g_ln2w, g_ln2b, g_w1, g_b1, g_w2, g_b2, cs_in = views
+
+    # fc2: x_out = x_mid + act.W2^T + b2
+    d_pre = _empty((M, ff), BF16, dev)
+    # x gelu' (saved by the forward epilogue) fused; the epilogue also accumulates the column sums of d_pre = the
+    # fc1 bias gradient
+    L.gemm(dxob, w2b, M, ff, d, b_mn=True, ldb=ff, out_bf16=d_pre, act=2, aux_in=gp, ld_aux=ff, colsum=g_b1)
+    with wg.after_main():
+        L.gemm(dxob, act, d, ff, M, a_mn=True, b_mn=True, lda=d, ldb=ff, out_f32=g_w2, k_splits=0)
+    if cs_out is not None:
+        g_b2 = cs_out
+    else:
+        L.colsum(dxob, M, d, g_b2)
+    # fc1: pre = u2.W1^T + b1
+    d_u2 = _empty((M, d), BF16, dev)
+    L.gemm(d_pre, w1b, M, d, ff, b_mn=True, ldb=d, out_bf16=d_u2)
+    with wg.after_main():
+        L.gemm(d_pre, u2, ff, d, M, a_mn=True, b_mn=True, lda=ff, ldb=d, out_f32=g_w1, k_splits=0)
+    # LN2 backward + residual branch
+    dxm = _empty((M, d), F32, dev)
+    dxmb = _empty((M, d), BF16, dev)
+    L.layernorm_bwd(d_u2, x_mid, stats[2], stats[3], ln2w.detach(), dxo, M, d, dxm, dxmb, g_ln2w, g_ln2b,
+                    dxsum=g_bo)  # colsum(dx_mid) is the out-proj bias gradient
+    del d_u2, x_mid
+    # attention output projection: x_mid = x + attn.Wo^T + bo
+    d_attn = _empty((M, d), BF16, dev)
+    L.gemm(dxmb, wob, M, d, d, b_mn=True, ldb=d, out_bf16=d_attn)
+    with wg.after_main():
+        L.gemm(dxmb, attn, d, d, M, a_mn=True, b_mn=True, lda=d, ldb=d, out_f32=g_wo, k_splits=0)
+    # attention core
+    dqkv = _empty((M, 3 * d), BF16, dev)
+    delta = _empty((B, H, S), F32, dev)
+    L.attn_bwd(qkv, attn, d_attn, lse, B, S, H, scale, delta, dqkv)
+    # fused QKV projection
+    d_u1 = _empty((M, d), BF16, dev)
+    L.gemm(dqkv, wqkv, M, d, 3 * d, b_mn=True, ldb=d, out_bf16=d_u1)
+    with wg.after_main():
+        L.gemm(dqkv, u1, 3 * d, d, M, a_mn=True, b_mn=True, lda=3 * d, ldb=d, out_f32=g_wqkv, k_splits=0)
+        L.colsum(dqkv, M, 3 * d, g_bqkv)
+    # LN1 backward + residual
+    dx = _empty((M, d), F32, dev)
+    dxb = _empty((M, d), BF16, dev)
+    L.layernorm_bwd(d_u1, x, stats[0], stats[1], ln1w.detach(), dxm, M, d, dx, dxb, g_ln1w, g_ln1b, dxsum=cs_in)
+    st.side.put(dx, dxb, cs_in)
+    wg.join()  # the weight gradients are complete on the current stream from here on
+    return dx, flat, (g_ln1w, g_ln1b, g_wqkv, g_bqkv, g_wo.view(d, d), g_bo, g_ln2w, g_ln2b, g_w1.view(ff, d), g_b1,
+                      g_w2.view(d, ff), g_b2)
+
+
 class BlockFn(torch.autograd.Function):
-    """One pre-LN transformer block (HF:348-366): x + Wo.Attn(LN1(x)) then + W2.gelu(W1.LN2(.))."""
+    """One pre-LN transformer block (HF:348-366) in HF's parameter layout: separate query / key / value weights, q and
+    v biases (the key has none, HF:222-224)."""
 
     @staticmethod
     def forward(ctx, x, ln1w, ln1b, wq, wk, wv, qb, vb, wo, bo, ln2w, ln2b, w1, b1, w2, b2, st: StepState, name, B, S,
                 H, eps):
-        dev = x.device
-        M, d = x.shape
-        ff = w1.shape[0]
         cache = st.cache
         wqkv, bqkv = cache.qkv(name + "qkv")
         wob, w1b, w2b = cache.weight(name + "wo"), cache.weight(name + "w1"), cache.weight(name + "w2")
-        scale = float((d // H) ** -0.5)
-
-        u1 = _empty((M, d), BF16, dev)
-        stats = _empty((4, M), F32, dev)
-        L.layernorm_fwd(x, ln1w.detach(), ln1b.detach(), eps, M, d, u1, stats[0], stats[1])
-        qkv = _empty((M, 3 * d), BF16, dev)
-        L.gemm(u1, wqkv, M, 3 * d, d, out_bf16=qkv, bias=bqkv)
-        attn = _empty((M, d), BF16, dev)
-        lse = _empty((B, H, S), F32, dev)
-        L.attn_fwd(qkv, B, S, H, scale, attn, lse)
-        x_mid = _empty((M, d), F32, dev)
-        L.gemm(attn, wob, M, d, d, out_f32=x_mid, bias=bo.detach(), res=x, ldr=d)
-        u2 = _empty((M, d), BF16, dev)
-        L.layernorm_fwd(x_mid, ln2w.detach(), ln2b.detach(), eps, M, d, u2, stats[2], stats[3])
-        gp = _empty((M, ff), BF16, dev)   # gelu'(pre-activation): all the backward needs of it
-        act = _empty((M, ff), BF16, dev)
-        L.gemm(u2, w1b, M, ff, d, out_bf16=act, bias=b1.detach(), act=1, aux_out=gp, ld_aux=ff)
-        x_out = _empty((M, d), F32, dev)
-        L.gemm(act, w2b, M, d, ff, out_f32=x_out, bias=b2.detach(), res=x_mid, ldr=d)
-
-        ctx.st, ctx.name, ctx.geom = st, name, (M, d, ff, B, S, H, scale)
-        ctx.saved = (x, u1, stats, qkv, attn, lse, x_mid, u2, gp, act, ln1w, ln2w, wqkv, wob, w1b, w2b)
-        return x_out
+        return _block_fwd(ctx, x, ln1w, ln1b, wqkv, bqkv, wob, bo, ln2w, ln2b, w1b, b1, w2b, b2, st, name, B, S, H, eps)
 
     @staticmethod
     def backward(ctx, dxo):
-        st = ctx.st
-        st.check()
-        M, d, ff, B, S, H, scale = ctx.geom
-        x, u1, stats, qkv, attn, lse, x_mid, u2, gp, act, ln1w, ln2w, wqkv, wob, w1b, w2b = ctx.saved
-        ctx.saved = None
-        dev = dxo.device
-        dxo = _contig_grad(dxo)
-        dxob, cs_out = st.side.take(dxo, M, d)
-        wg = _SideStream(dev) if _WGRAD_STREAM else _NoSideStream()  # operands stay referenced until wg.join() below
-
-        # every atomically-accumulated output of this block in one zero-filled buffer (one memset); the last slot
-        # collects colsum(dx) of this block's input gradient for the stage upstream
-        sizes = [d, d, 3 * d * d, 3 * d, d * d, d, d, d, ff * d, ff, d * ff, d, d]
-        flat = torch.zeros(sum(sizes), dtype=F32, device=dev)
-        views, o = [], 0
-        for s_ in sizes:
-            views.append(flat[o:o + s_])
-            o += s_
-        g_ln1w, g_ln1b, g_wqkv, g_bqkv, g_wo, g_bo, g_ln2w, g_ln2b, g_w1, g_b1, g_w2, g_b2, cs_in = views
-
-        # fc2: x_out = x_mid + act.W2^T + b2
-        d_pre = _empty((M, ff), BF16, dev)
-        # x gelu' (saved by the forward epilogue) fused; the epilogue also accumulates the column sums of d_pre = the
-        # fc1 bias gradient
-        L.gemm(dxob, w2b, M, ff, d, b_mn=True, ldb=ff, out_bf16=d_pre, act=2, aux_in=gp, ld_aux=ff, colsum=g_b1)
-        with wg.after_main():
-            L.gemm(dxob, act, d, ff, M, a_mn=True, b_mn=True, lda=d, ldb=ff, out_f32=g_w2, k_splits=0)
-        if cs_out is not None:
-            g_b2 = cs_out
-        else:
-            L.colsum(dxob, M, d, g_b2)
-        # fc1: pre = u2.W1^T + b1
-        d_u2 = _empty((M, d), BF16, dev)
-        L.gemm(d_pre, w1b, M, d, ff, b_mn=True, ldb=d, out_bf16=d_u2)
-        with wg.after_main():
-            L.gemm(d_pre, u2, ff, d, M, a_mn=True, b_mn=True, lda=ff, ldb=d, out_f32=g_w1, k_splits=0)
-        # LN2 backward + residual branch
-        dxm = _empty((M, d), F32, dev)
-        dxmb = _empty((M, d), BF16, dev)
-        L.layernorm_bwd(d_u2, x_mid, stats[2], stats[3], ln2w.detach(), dxo, M, d, dxm, dxmb, g_ln2w, g_ln2b,
-                        dxsum=g_bo)  # colsum(dx_mid) is the out-proj bias gradient
-        del d_u2, x_mid
-        # attention output projection: x_mid = x + attn.Wo^T + bo
-        d_attn = _empty((M, d), BF16, dev)
-        L.gemm(dxmb, wob, M, d, d, b_mn=True, ldb=d, out_bf16=d_attn)
-        with wg.after_main():
-            L.gemm(dxmb, attn, d, d, M, a_mn=True, b_mn=True, lda=d, ldb=d, out_f32=g_wo, k_splits=0)
-        # attention core
-        dqkv = _empty((M, 3 * d), BF16, dev)
-        delta = _empty((B, H, S), F32, dev)
-        L.attn_bwd(qkv, attn, d_attn, lse, B, S, H, scale, delta, dqkv)
-        # fused QKV projection
-        d_u1 = _empty((M, d), BF16, dev)
-        L.gemm(dqkv, wqkv, M, d, 3 * d, b_mn=True, ldb=d, out_bf16=d_u1)
-        with wg.after_main():
-            L.gemm(dqkv, u1, 3 * d, d, M, a_mn=True, b_mn=True, lda=3 * d, ldb=d, out_f32=g_wqkv, k_splits=0)
-            L.colsum(dqkv, M, 3 * d, g_bqkv)
-        # LN1 backward + residual
-        dx = _empty((M, d), F32, dev)
-        dxb = _empty((M, d), BF16, dev)
-        L.layernorm_bwd(d_u1, x, stats[0], stats[1], ln1w.detach(), dxm, M, d, dx, dxb, g_ln1w, g_ln1b, dxsum=cs_in)
-        st.side.put(dx, dxb, cs_in)
-        wg.join()  # the weight gradients are complete on the current stream from here on
-
+        d = ctx.geom[1]
+        dx, flat, (g_ln1w, g_ln1b, g_wqkv, g_bqkv, g_wo, g_bo, g_ln2w, g_ln2b, g_w1, g_b1, g_w2, g_b2) = \
+            _block_bwd(ctx, dxo)
         gw = g_wqkv.view(3, d, d)
-        grads = (g_ln1w, g_ln1b, gw[0], gw[1], gw[2], g_bqkv[0:d], g_bqkv[2 * d:3 * d], g_wo.view(d, d), g_bo,
-                 g_ln2w, g_ln2b, g_w1.view(ff, d), g_b1, g_w2.view(d, ff), g_b2)
-        st.reduce(flat, ctx.name, grads)
+        grads = (g_ln1w, g_ln1b, gw[0], gw[1], gw[2], g_bqkv[0:d], g_bqkv[2 * d:3 * d], g_wo, g_bo, g_ln2w, g_ln2b, g_w1,
+                 g_b1, g_w2, g_b2)
+        ctx.st.reduce(flat, ctx.name, grads)
+        return (dx,) + grads + (None, None, None, None, None, None)
+
+
+class FusedQkvBlockFn(torch.autograd.Function):
+    """The same block in the predictive path's layout (pretraining/predictive/vision_transformer.py:186-231): ONE
+    `qkv = nn.Linear(dim, 3 dim, bias=qkv_bias)` whose output reshapes to [B, N, 3, heads, head_dim] -- exactly the
+    fused-QKV layout of the attention kernels -- LayerNorm eps 1e-6, MLP fc1 / GELU / fc2.  bqkv may be None."""
+
+    @staticmethod
+    def forward(ctx, x, ln1w, ln1b, wqkv, bqkv, wo, bo, ln2w, ln2b, w1, b1, w2, b2, st: StepState, name, B, S, H, eps):
+        cache = st.cache
+        ctx.has_qkv_bias = bqkv is not None
+        return _block_fwd(ctx, x, ln1w, ln1b, cache.weight(name + "qkv"), bqkv.detach() if bqkv is not None else None,
+                          cache.weight(name + "wo"), bo, ln2w, ln2b, cache.weight(name + "w1"), b1,
+                          cache.weight(name + "w2"), b2, st, name, B, S, H, eps)
+
+    @staticmethod
+    def backward(ctx, dxo):
+        d = ctx.geom[1]
+        dx, flat, (g_ln1w, g_ln1b, g_wqkv, g_bqkv, g_wo, g_bo, g_ln2w, g_ln2b, g_w1, g_b1, g_w2, g_b2) = \
+            _block_bwd(ctx, dxo)
+        grads = (g_ln1w, g_ln1b, g_wqkv.view(3 * d, d), g_bqkv if ctx.has_qkv_bias else None, g_wo, g_bo, g_ln2w, g_ln2b,
+                 g_w1, g_b1, g_w2, g_b2)
+        ctx.st.reduce(flat, ctx.name, grads)
         return (dx,) + grads + (None, None, None, None, None, None)
 
 

@@ -333,6 +333,58 @@ class VideoMAEForPreTraining(nn.Module):
             self._status.zero_()
             raise ValueError("bool_masked_pos: every row must mask the same number of tokens (HF:121-122 reshape)")
 
+    # -- the un-masked encoder pass ---------------------------------------------------------------------------------
+    def encode(self, pixel_values):
+        """`VideoMAEModel.forward(pixel_values, bool_masked_pos=None).last_hidden_state` (HF:420-470 with
+        use_mean_pooling=True, i.e. no final LayerNorm): ALL N tokens through the patch embedding (+ sinusoid table) and
+        the encoder blocks -- the pass benchmarks/compute_embeddings_videomae.py:261 runs on a pretrained checkpoint
+        (its VideoMAEForVideoClassification head -- mean over tokens, fc_norm, classifier -- stays the caller's).
+        Same kernels as the training step at S = N (1568) tokens, 12 heads.  -> fp32 [B, N, hidden]."""
+        c = self.config
+        if pixel_values.dim() != 5:
+            raise ValueError("pixel_values must be [batch, frames, channels, height, width]")
+        B, T, C, H, W = pixel_values.shape
+        if C != c.num_channels:
+            raise ValueError("Make sure that the channel dimension of the pixel values match with the one set in the "
+                             "configuration.")
+        if H != c.image_size or W != c.image_size or T != c.num_frames:
+            raise ValueError(f"expected [{c.num_frames}, {c.num_channels}, {c.image_size}, {c.image_size}] clips")
+        if not pixel_values.is_cuda:
+            raise L.BvcError("VideoMAEForPreTraining (bvc-b200) runs on CUDA only; there is no CPU path")
+        dev = pixel_values.device
+        N = self.num_patches
+        x = pixel_values.detach()
+        if x.dtype == torch.uint8:
+            if self._pixel_norm is None:
+                raise ValueError("uint8 pixel_values need model.set_input_normalization(mean, std) first")
+            x = x.contiguous()
+        elif x.dtype != F32 or not x.is_contiguous():
+            x = x.to(F32).contiguous()
+        with torch.cuda.device(dev):
+            st = StepState(self._cache)
+            st.B, st.N, st.nv, st.nm = B, N, N, 0
+            st.status = torch.zeros(1, dtype=torch.int32, device=dev)
+            st.vis_idx = torch.empty((B, N), dtype=torch.int32, device=dev)
+            st.msk_idx = torch.empty((1,), dtype=torch.int32, device=dev)
+            st.slot = torch.empty((B, N), dtype=torch.int32, device=dev)
+            L.mask_to_index(torch.zeros((B, N), dtype=torch.uint8, device=dev), N, st.vis_idx, st.msk_idx, st.slot,
+                            st.status)
+            K = C * c.tubelet_size * c.patch_size ** 2
+            patches = torch.empty((B * N, K), dtype=BF16, device=dev)
+            L.patchify_target(x, st.slot, c.tubelet_size, c.patch_size, N, patches,
+                              torch.empty((1, K), dtype=F32, device=dev), False,
+                              pixel_norm=self._pixel_norm if x.dtype == torch.uint8 else None)
+            pos_e, _ = self._pos(dev)
+            proj = self.videomae.embeddings.patch_embeddings.projection
+            self._cache.register(self._weight_entries(), dev)
+            self._cache.refresh()
+            st.epoch = self._cache.epoch
+            h = EmbedFn.apply(proj.weight, proj.bias, patches, pos_e, st, "pe")
+            for i, layer in enumerate(self.videomae.encoder.layer):
+                h = BlockFn.apply(h, *layer.flat_params(), st, f"e{i}.", B, N, c.num_attention_heads,
+                                  float(c.layer_norm_eps))
+        return h.view(B, N, c.hidden_size)
+
     # -- the hot path -------------------------------------------------------------------------------------------------
     def forward(self, pixel_values, bool_masked_pos=None, **kwargs):
         c = self.config

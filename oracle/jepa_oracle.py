@@ -46,3 +46,41 @@ def ema_update(params_q, params_k, m):
     mf = torch.tensor(m, dtype=torch.float64).to(torch.float32)
     omf = torch.tensor(1.0 - m, dtype=torch.float64).to(torch.float32)
     return [(k * mf) + (q * omf) for q, k in zip(params_q, params_k)]
+
+
+def vit_block(x, p, num_heads, eps=1e-6):
+    """vision_transformer.py:186-231 -- `Block.forward`: y = x + proj(softmax(q k^T * scale) v) with ONE fused qkv Linear
+    reshaped [B, N, 3, heads, head_dim] (:200), then y + fc2(gelu(fc1(norm2(y)))) (:167-183, exact-erf nn.GELU).
+    `p` maps the block's state-dict names (norm1.weight, attn.qkv.weight, ..., mlp.fc2.bias) to tensors; attn.qkv.bias
+    may be absent (qkv_bias=False).  Computes in the dtype of x / p."""
+    import torch.nn.functional as F
+    B, N, C = x.shape
+    hd = C // num_heads
+    u = F.layer_norm(x, (C,), p["norm1.weight"], p["norm1.bias"], eps)
+    qkv = F.linear(u, p["attn.qkv.weight"], p.get("attn.qkv.bias")).reshape(B, N, 3, num_heads, hd).permute(2, 0, 3, 1, 4)
+    q, k, v = qkv[0], qkv[1], qkv[2]
+    attn = ((q @ k.transpose(-2, -1)) * hd ** -0.5).softmax(dim=-1)
+    y = (attn @ v).transpose(1, 2).reshape(B, N, C)
+    x = x + F.linear(y, p["attn.proj.weight"], p["attn.proj.bias"])
+    u = F.layer_norm(x, (C,), p["norm2.weight"], p["norm2.bias"], eps)
+    return x + F.linear(F.gelu(F.linear(u, p["mlp.fc1.weight"], p["mlp.fc1.bias"])), p["mlp.fc2.weight"], p["mlp.fc2.bias"])
+
+
+def vit_block_params(dim, mlp_ratio=4.0, seed=0, qkv_bias=True):
+    """Seeded 'trained-like' parameters of one block (state-dict names of vision_transformer.Block)."""
+    g = torch.Generator().manual_seed(seed)
+    ff = int(dim * mlp_ratio)
+    shapes = {"norm1.weight": (dim,), "norm1.bias": (dim,), "attn.qkv.weight": (3 * dim, dim), "attn.qkv.bias": (3 * dim,),
+              "attn.proj.weight": (dim, dim), "attn.proj.bias": (dim,), "norm2.weight": (dim,), "norm2.bias": (dim,),
+              "mlp.fc1.weight": (ff, dim), "mlp.fc1.bias": (ff,), "mlp.fc2.weight": (dim, ff), "mlp.fc2.bias": (dim,)}
+    out = {}
+    for k, s in shapes.items():
+        if k == "attn.qkv.bias" and not qkv_bias:
+            continue
+        if k.startswith("norm") and k.endswith("weight"):
+            out[k] = 1.0 + 0.2 * torch.randn(s, generator=g)
+        elif k.endswith("weight"):
+            out[k] = 0.08 * torch.randn(s, generator=g)
+        else:
+            out[k] = 0.1 * torch.randn(s, generator=g)
+    return out

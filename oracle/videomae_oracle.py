@@ -349,3 +349,17 @@ def grads_of(params, pixel_values, mask, cfg, grad_scale=1.0):
     loss, logits = forward_loss(ps, pixel_values, mask, cfg)
     (loss * grad_scale).backward()
     return loss.detach(), logits.detach(), {k: v.grad for k, v in ps.items()}
+
+
+def encode_unmasked(params, pixel_values, cfg: OracleConfig):
+    """HF VideoMAEModel.forward with bool_masked_pos=None (HF:420-470: embeddings of ALL tokens + sinusoid table, the
+    encoder blocks, no final LayerNorm under use_mean_pooling=True) -- the un-masked encoder pass of
+    benchmarks/compute_embeddings_videomae.py:261.  -> last_hidden_state [B, N, hidden]."""
+    p = params
+    patches = patchify_embed_order(pixel_values, cfg).to(p["videomae.embeddings.patch_embeddings.projection.weight"].dtype)
+    w = p["videomae.embeddings.patch_embeddings.projection.weight"]
+    h = F.linear(patches, w.reshape(w.shape[0], -1), p["videomae.embeddings.patch_embeddings.projection.bias"])
+    h = h + sinusoid_table(cfg.seq_len, cfg.hidden_size).to(h.dtype)[None]
+    for i in range(cfg.num_hidden_layers):
+        h = block_forward(h, p, f"videomae.encoder.layer.{i}.", cfg.num_attention_heads, cfg.layer_norm_eps)
+    return h

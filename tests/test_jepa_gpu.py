@@ -111,3 +111,123 @@ def test_jepa_edge_cases():
     lr = torch.nn.functional.smooth_l1_loss(zr, h.cpu().double(), beta=0.5)
     lr.backward()
     assert abs(float(l) - float(lr)) < 1e-6 and float((z.grad.cpu().double() - zr.grad).abs().max()) < 1e-7
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# the predictive path's ViT block on the VideoMAE step's kernels (bvc_b200.jepa_vit)
+class _RefLikeAttention(torch.nn.Module):
+    """Structure of vision_transformer.py:186-197 (the reference tree is absent on the GPU box)."""
+
+    def __init__(self, dim, heads, qkv_bias):
+        super().__init__()
+        self.num_heads, self.scale = heads, (dim // heads) ** -0.5
+        self.qkv = torch.nn.Linear(dim, 3 * dim, bias=qkv_bias)
+        self.attn_drop = torch.nn.Dropout(0.)
+        self.proj = torch.nn.Linear(dim, dim)
+        self.proj_drop = torch.nn.Dropout(0.)
+
+
+class _RefLikeMLP(torch.nn.Module):
+    def __init__(self, dim, ff):
+        super().__init__()
+        self.fc1, self.act, self.fc2, self.drop = torch.nn.Linear(dim, ff), torch.nn.GELU(), torch.nn.Linear(ff, dim), torch.nn.Dropout(0.)
+
+
+class _RefLikeBlock(torch.nn.Module):
+    def __init__(self, dim, heads, qkv_bias):
+        super().__init__()
+        self.norm1 = torch.nn.LayerNorm(dim, eps=1e-6)
+        self.attn = _RefLikeAttention(dim, heads, qkv_bias)
+        self.drop_path = torch.nn.Identity()
+        self.norm2 = torch.nn.LayerNorm(dim, eps=1e-6)
+        self.mlp = _RefLikeMLP(dim, 4 * dim)
+
+
+@pytest.mark.parametrize("tag", ["d128", "d192_nobias"])
+def test_jepa_vit_block_matches_reference_fixture_and_oracle(golden_dir, tag):
+    """bvc_b200.jepa_vit.Block (fused qkv Linear, LayerNorm eps 1e-6) against the fp64 output / gradients of the
+    reference's own Block (fixture) and the live oracle.  Tolerances: bf16 operands, fp32 accumulation -- output
+    rel-L2 5e-3, input gradient 1.5e-2, parameter gradients 2e-2 per tensor (norms 5e-3)."""
+    import os
+    from functools import partial
+    import bvc_b200 as bvc
+    from tests.helpers import rel_l2
+    dev = _dev()
+    g = np.load(os.path.join(golden_dir, "jepa_vit_block.npz"))
+    dim, heads, B, N, qkv_bias = (int(v) for v in g[f"{tag}.meta"])
+    params = J.vit_block_params(dim, seed=7, qkv_bias=bool(qkv_bias))
+    gen = torch.Generator().manual_seed(11)
+    x = torch.randn(B, N, dim, generator=gen) * 1.5 + 0.2
+    w = torch.randn(B, N, dim, generator=gen)
+    blk = bvc.jepa_vit.Block(dim, heads, mlp_ratio=4.0, qkv_bias=bool(qkv_bias),
+                             norm_layer=partial(torch.nn.LayerNorm, eps=1e-6))
+    blk.load_state_dict(params, strict=True)
+    blk = blk.to(dev)
+    xd = x.to(dev).requires_grad_(True)
+    y = blk(xd)
+    (y * w.to(dev)).sum().backward()
+    assert rel_l2(y.detach().cpu(), torch.from_numpy(g[f"{tag}.y"])) <= 5e-3
+    assert rel_l2(xd.grad.cpu(), torch.from_numpy(g[f"{tag}.dx"])) <= 1.5e-2
+    for k, p in blk.named_parameters():
+        n_ref = float(g[f"{tag}.gradnorm.{k}"])
+        assert abs(float(p.grad.double().norm()) - n_ref) <= 5e-3 * n_ref, k
+        if f"{tag}.grad.{k}" in g.files:
+            assert rel_l2(p.grad.cpu(), torch.from_numpy(g[f"{tag}.grad.{k}"])) <= 2e-2, k
+    # live oracle (fp64) on the same inputs
+    pd = {k: v.double() for k, v in params.items()}
+    assert rel_l2(y.detach().cpu(), J.vit_block(x.double(), pd, heads, eps=1e-6)) <= 5e-3
+    # from_reference: adopts the sub-modules of a reference-structured block (parameters shared, state-dict keys equal)
+    ref_like = _RefLikeBlock(dim, heads, bool(qkv_bias))
+    ref_like.load_state_dict(params, strict=True)
+    ref_like = ref_like.to(dev)
+    holder = torch.nn.Module()
+    holder.blocks = torch.nn.ModuleList([ref_like])
+    bvc.jepa_vit.convert_blocks(holder)
+    conv = holder.blocks[0]
+    assert isinstance(conv, bvc.jepa_vit.Block) and conv.attn.qkv.weight is ref_like.attn.qkv.weight
+    assert set(conv.state_dict()) == set(params)
+    y2 = conv(x.to(dev))
+    assert torch.equal(y2, y.detach())
+    # two chained blocks: the activation-gradient side channel (bf16 twin + column sums) is shared between them
+    blk2 = bvc.jepa_vit.Block(dim, heads, qkv_bias=bool(qkv_bias), norm_layer=partial(torch.nn.LayerNorm, eps=1e-6))
+    blk2.load_state_dict(params, strict=True)
+    blk2 = blk2.to(dev)
+    blk.zero_grad(set_to_none=True)
+    xc = x.to(dev).requires_grad_(True)
+    (blk2(blk(xc)) * w.to(dev)).sum().backward()
+    xo = x.double().requires_grad_(True)
+    (J.vit_block(J.vit_block(xo, pd, heads, eps=1e-6), pd, heads, eps=1e-6) * w.double()).sum().backward()
+    assert rel_l2(xc.grad.cpu(), xo.grad) <= 2e-2
+
+
+def test_unmasked_encoder_pass(golden_dir):
+    """model.encode(x) == HF VideoMAEModel(bool_masked_pos=None).last_hidden_state (compute_embeddings_videomae.py:261):
+    tiny configuration against the HF-made fixture and the live oracle, and ViT-S at ALL 1568 tokens against the live
+    oracle (fp32 CPU).  Tolerance: rel-L2 6e-3 (bf16 operands through 12 blocks)."""
+    import os
+    import bvc_b200 as bvc
+    from oracle import videomae_oracle as O
+    from tests.helpers import bvc_config, rel_l2
+    dev = _dev()
+    g = np.load(os.path.join(golden_dir, "tiny_encode.npz"))
+    cfg = O.make_config("tiny")
+    params = O.init_params(cfg, seed=1, perturb=True)
+    x = O.synthetic_clip(2, cfg, seed=9, image_like=True)
+    model = bvc.VideoMAEForPreTraining(bvc_config(cfg))
+    model.load_state_dict(params, strict=True)
+    model = model.to(dev).eval()
+    with torch.no_grad():
+        h = model.encode(x.to(dev))
+    assert h.shape == (2, cfg.seq_len, cfg.hidden_size) and h.dtype == torch.float32
+    assert rel_l2(h.cpu(), torch.from_numpy(g["last_hidden_state"])) <= 6e-3
+    cfg = O.make_config("small")
+    params = O.init_params(cfg, seed=2, perturb=True)
+    x = O.synthetic_clip(2, cfg, seed=3, image_like=True)
+    model = bvc.VideoMAEForPreTraining(bvc_config(cfg))
+    model.load_state_dict(params, strict=True)
+    model = model.to(dev).eval()
+    with torch.no_grad():
+        h = model.encode(x.to(dev))
+        ref = O.encode_unmasked(params, x, cfg)
+    assert h.shape == (2, 1568, 384)
+    assert rel_l2(h.cpu(), ref) <= 6e-3

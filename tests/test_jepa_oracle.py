@@ -63,3 +63,36 @@ def test_mask_collator_mirror_reproduces_the_reference_masks(tag, B, seed):
     assert torch.equal(torch.stack(list(m_pred)), torch.from_numpy(g["masks_pred"]))
     assert int(torch.stack(list(m_pred)).min()) >= 7 * 196 and int(torch.stack(list(m_enc)).max()) < 196
     assert coll.step() == 1   # the shared counter advanced once for the batch above
+
+
+@pytest.mark.parametrize("tag", ["d128", "d192_nobias"])
+def test_vit_block_oracle_matches_reference_block(golden_dir, tag):
+    """oracle.jepa_oracle.vit_block against the fp64 output / gradients of the reference's own `Block`
+    (vision_transformer.py:213-231, fixtures by tools/make_golden_jepa_vit.py)."""
+    import os
+    g = np.load(os.path.join(golden_dir, "jepa_vit_block.npz"))
+    dim, heads, B, N, qkv_bias = (int(v) for v in g[f"{tag}.meta"])
+    params = {k: v.double().requires_grad_(True) for k, v in J.vit_block_params(dim, seed=7, qkv_bias=bool(qkv_bias)).items()}
+    gen = torch.Generator().manual_seed(11)
+    x = (torch.randn(B, N, dim, generator=gen) * 1.5 + 0.2).double().requires_grad_(True)
+    w = torch.randn(B, N, dim, generator=gen).double()
+    y = J.vit_block(x, params, heads, eps=1e-6)
+    (y * w).sum().backward()
+    np.testing.assert_allclose(y.detach().numpy(), g[f"{tag}.y"], rtol=0, atol=2e-6)
+    np.testing.assert_allclose(x.grad.numpy(), g[f"{tag}.dx"], rtol=0, atol=2e-5)
+    for k, p in params.items():
+        np.testing.assert_allclose(float(p.grad.norm()), float(g[f"{tag}.gradnorm.{k}"]), rtol=1e-9)
+        if f"{tag}.grad.{k}" in g.files:
+            np.testing.assert_allclose(p.grad.numpy(), g[f"{tag}.grad.{k}"], rtol=0, atol=1e-5 * float(g[f"{tag}.gradnorm.{k}"]) + 1e-7)
+
+
+def test_unmasked_encoder_oracle_matches_hf_fixture(golden_dir):
+    """oracle.videomae_oracle.encode_unmasked against transformers.VideoMAEModel(bool_masked_pos=None) (HF:420-470)."""
+    import os
+    from oracle import videomae_oracle as O
+    g = np.load(os.path.join(golden_dir, "tiny_encode.npz"))
+    cfg = O.make_config("tiny")
+    params = O.init_params(cfg, seed=1, perturb=True)
+    x = O.synthetic_clip(2, cfg, seed=9, image_like=True)
+    h = O.encode_unmasked(params, x, cfg)
+    np.testing.assert_allclose(h.numpy(), g["last_hidden_state"], rtol=0, atol=5e-5)

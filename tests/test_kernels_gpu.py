@@ -5,6 +5,8 @@ GELU / GELU' / residual / row-gather / segment scatter / fused MSE / fused colum
 segment remaps, column sums, casts, decoder mask rows, tube-mask indexing + patchify + normalised-pixel target
 (bit-exact indices and visible-patch rows), attention forward / backward at S = 8 ... 1568 incl. ragged tiles and the
 short-sequence kernel of attn_small.cu).
+Group "benchshapes" runs the kernel shapes of the benchmark step itself (ViT-B/16 at batch 64: M = 10240 / 100352 /
+90112 rows, attention at B64 S160 H12 and B64 S1568 H6, patchify at B = 64) with the tile shapes the dispatcher picks.
 Each group runs in its own process so that a device trap in one group cannot poison the others; a group passes when
 every case printed PASS.  The end-to-end step parity lives in test_model_gpu.py."""
 import os
@@ -17,10 +19,11 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("group", ["rows", "patchify", "gemm00", "gemm01", "gemm10", "gemm11", "gemmx", "gemmpair", "attn"])
+@pytest.mark.parametrize("group", ["rows", "patchify", "gemm00", "gemm01", "gemm10", "gemm11", "gemmx", "gemmpair", "attn",
+                                   "benchshapes"])
 def test_kernel_group(group):
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "gpu_selftest.py"), group], capture_output=True,
-                       text=True, timeout=600)
+                       text=True, timeout=900)
     lines = [ln for ln in r.stdout.splitlines() if ln.startswith(("PASS", "FAIL", "SELFTEST"))]
     fails = [ln for ln in lines if ln.startswith("FAIL")]
     assert r.returncode == 0 and not fails and any(ln.startswith("SELFTEST") for ln in lines), \

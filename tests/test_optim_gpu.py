@@ -110,3 +110,87 @@ def test_fused_sgd_refreshes_weight_copies():
     assert losses[0][1] < losses[0][0]
     for a, b in zip(*losses):
         assert abs(a - b) <= 2e-5 * abs(a), losses
+
+
+@pytest.mark.parametrize("cls_name,kw", [("AdamW", dict(lr=1e-3, betas=(0.9, 0.95), weight_decay=0.05)),   # the reference's
+                                         ("AdamW", dict(lr=3e-3, betas=(0.8, 0.99), eps=1e-6, weight_decay=0.0)),
+                                         ("Adam", dict(lr=1e-3, betas=(0.9, 0.999), weight_decay=1e-2)),
+                                         ("Adam", dict(lr=2e-3))])
+def test_fused_adam_matches_torch(cls_name, kw):
+    """FusedAdamW / FusedAdam (bvc_adam_step) against torch.optim.AdamW / Adam (pretrain_videomae.py:190-193: AdamW with
+    betas (0.9, 0.95)): parameters and both moments after 5 steps.  Same operation order as torch's single-tensor path,
+    scalars in double; what differs is fma contraction -- a few ulp per step: rtol 5e-6 / atol 1e-7."""
+    import bvc_b200 as bvc
+    dev = torch.device("cuda:0")
+    pa, pb = _params(2, dev), _params(2, dev)
+    oa = getattr(torch.optim, cls_name)(pa, **kw)
+    ob = getattr(bvc, "Fused" + cls_name)(pb, **kw)
+    for step in range(5):
+        for p, q, g in zip(pa, pb, _grads(30 + step, dev)):
+            p.grad, q.grad = g.clone(), g.clone()
+        oa.step()
+        ob.step()
+    torch.cuda.synchronize()
+    for p, q in zip(pa, pb):
+        assert torch.allclose(p, q, rtol=5e-6, atol=1e-7), float((p - q).abs().max())
+        for k in ("exp_avg", "exp_avg_sq"):
+            assert torch.allclose(oa.state[p][k], ob.state[q][k], rtol=5e-6, atol=1e-9), k
+        assert float(ob.state[q]["step"]) == float(oa.state[p]["step"]) == 5.0
+    assert set(ob.state_dict()["state"][0]) == set(oa.state_dict()["state"][0])  # checkpoints interchange
+    # ... and do: torch's state loads into the fused optimizer and both continue identically
+    oc = getattr(bvc, "Fused" + cls_name)(_params(2, dev), **kw)
+    with torch.no_grad():
+        for p, q in zip(pa, oc.param_groups[0]["params"]):
+            q.copy_(p)
+    oc.load_state_dict(oa.state_dict())
+    for p, q, g in zip(pa, oc.param_groups[0]["params"], _grads(40, dev)):
+        p.grad, q.grad = g.clone(), g.clone()
+    oa.step()
+    oc.step()
+    for p, q in zip(pa, oc.param_groups[0]["params"]):
+        assert torch.allclose(p, q, rtol=5e-6, atol=1e-7)
+
+
+@pytest.mark.parametrize("opt_name", ["SGD", "AdamW"])
+def test_scaler_step_is_two_launches_and_matches_torch(opt_name):
+    """scaler.step(optimizer) through the `grad_scaler` hand-over: the inf / nan check is ONE read-only launch
+    (bvc_grad_nonfinite), the update another; same parameters, same scale trajectory and same skipped steps as torch's
+    optimizer under the same GradScaler, and a torch SGD state dict saved BEFORE its first step
+    (momentum_buffer = None) loads."""
+    import bvc_b200 as bvc
+    from bvc_b200 import _lib as L
+    dev = torch.device("cuda:0")
+    kw = dict(lr=0.1, momentum=0.9, nesterov=True) if opt_name == "SGD" else dict(lr=1e-3, betas=(0.9, 0.95), weight_decay=0.05)
+    pa, pb = _params(3, dev), _params(3, dev)
+    oa = getattr(torch.optim, opt_name)(pa, **kw)
+    ob = getattr(bvc, "Fused" + opt_name)(pb, **kw)
+    if opt_name == "SGD":
+        for p, g in zip(pa, _grads(1, dev)):
+            p.grad = g
+        fresh = torch.optim.SGD(pa, **kw)
+        sd = fresh.state_dict()          # no step yet: empty state
+        ob.load_state_dict(sd)
+    sa, sb = torch.amp.GradScaler("cuda", init_scale=256.0, growth_interval=2), \
+        torch.amp.GradScaler("cuda", init_scale=256.0, growth_interval=2)
+    for step in range(6):
+        scale_now = float(sa.get_scale())
+        gs = _grads(50 + step, dev, scale=scale_now)
+        if step in (0, 3):
+            gs[4][7, 5] = float("nan") if step == 0 else float("-inf")
+        for p, q, g in zip(pa, pb, gs):
+            p.grad, q.grad = g.clone(), g.clone()
+        sa.scale(torch.ones((), device=dev))
+        sb.scale(torch.ones((), device=dev))
+        sa.step(oa)
+        n0 = L.launch_count()
+        sb.step(ob)
+        assert L.launch_count() - n0 == (2 if opt_name == "SGD" else 3)  # check + update (+ Adam's step counter)
+        sa.update()
+        sb.update()
+        assert sa.get_scale() == sb.get_scale(), step
+    torch.cuda.synchronize()
+    for p, q in zip(pa, pb):
+        assert torch.isfinite(q).all()
+        assert torch.allclose(p, q, rtol=5e-6, atol=2e-6), float((p - q).abs().max())
+    if opt_name == "AdamW":
+        assert float(ob.state[pb[0]]["step"]) == 4.0   # two of the six steps were skipped

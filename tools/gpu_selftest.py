@@ -109,6 +109,42 @@ def gemm_case(M, N, K, a_mn, b_mn, bn, mode="plain", ks=1, pair=0):
         want = ref + res.double() + bias.double()
         e1, e2 = relerr(of, want), relerr(ob.float(), want)
         report(name, e1 < 1e-5 and e2 < 5e-3, f"f32 {e1:.2e} bf16 {e2:.2e}")
+    elif mode == "bias_bf16":
+        # the engine's QKV projection (EPI_PLAIN: bf16 output only, bias)
+        bias = torch.randn(N, device=dev, generator=g)
+        ob = torch.zeros(M, N, device=dev, dtype=torch.bfloat16)
+        L.gemm(a_store, b_store, M, N, K, out_bf16=ob, bias=bias, **kw)
+        e2 = relerr(ob.float(), ref + bias.double())
+        report(name, e2 < 5e-3, f"bf16 {e2:.2e}")
+    elif mode == "res_f32":
+        # exactly the engine's residual GEMMs (EPI_RES: fp32 output only, bias + fp32 residual rows)
+        res = torch.randn(M, N, device=dev, generator=g)
+        bias = torch.randn(N, device=dev, generator=g)
+        of = torch.zeros(M, N, device=dev)
+        L.gemm(a_store, b_store, M, N, K, out_f32=of, res=res, ldr=N, bias=bias, **kw)
+        e1 = relerr(of, ref + res.double() + bias.double())
+        report(name, e1 < 1e-5, f"f32 {e1:.2e}")
+    elif mode == "gelu_bwd_colsum":
+        # the engine's fc2 dgrad: x gelu' (saved factor) with the fc1 bias gradient (column sums) fused
+        gp = bf(torch.randn(M, N, device=dev, generator=g))
+        ob = torch.zeros(M, N, device=dev, dtype=torch.bfloat16)
+        cs = torch.zeros(N, device=dev)
+        L.gemm(a_store, b_store, M, N, K, out_bf16=ob, act=2, aux_in=gp, ld_aux=N, alpha=0.05, colsum=cs, **kw)
+        want = 0.05 * ref * gp.double()
+        e, ec = relerr(ob.float(), want), relerr(cs, want.sum(0))
+        report(name, e < 5e-3 and ec < 2e-3, f"{e:.2e} colsum {ec:.2e}")
+    elif mode == "loss_nologits":
+        tgt = torch.randn(M, N, device=dev, generator=g)
+        bias = torch.randn(N, device=dev, generator=g)
+        part = torch.full((L.gemm_loss_slots(M, N, bn),), float("nan"), device=dev)
+        diff = torch.zeros(M, N, device=dev, dtype=torch.bfloat16)
+        L.gemm(a_store, b_store, M, N, K, out_bf16=diff, bias=bias, target=tgt, ldt=N, loss_partial=part, alpha=0.1, **kw)
+        loss = torch.zeros(1, device=dev)
+        L.loss_finalize(part, M * N, torch.zeros(1, device=dev, dtype=torch.int32), loss)
+        lg = 0.1 * ref + bias.double()
+        want = ((lg - tgt.double()) ** 2).mean()
+        e0, e1 = abs(float(loss) - float(want)) / float(want), relerr(diff.float(), lg - tgt.double())
+        report(name, e0 < 1e-5 and e1 < 5e-3, f"loss {e0:.2e} diff {e1:.2e}")
     elif mode == "loss":
         tgt = torch.randn(M, N, device=dev, generator=g)
         bias = torch.randn(N, device=dev, generator=g)
@@ -331,20 +367,34 @@ def attn_case(B, S, H, seed=0):
     lse = torch.zeros(B, H, S, device=dev)
     scale = 64 ** -0.5
     L.attn_fwd(qkv, B, S, H, scale, out, lse)
-    q, k, v = (qkv[:, :, i].permute(0, 2, 1, 3).double().requires_grad_(True) for i in range(3))
-    s = (q @ k.transpose(-1, -2)) * scale
-    ref = torch.softmax(s, -1) @ v
-    e = relerr(out.float().view(B, S, H, 64).permute(0, 2, 1, 3), ref)
-    el = relerr(lse, torch.logsumexp(s, -1))
-    report(f"attn_fwd B{B} S{S} H{H}", e < 6e-3 and el < 1e-4, f"out {e:.2e} lse {el:.2e}")
     do = bf(torch.randn(B, S, d, device=dev, generator=g))
     dqkv = torch.zeros_like(qkv)
     delta = torch.zeros(B, H, S, device=dev)
     L.attn_bwd(qkv, out, do, lse, B, S, H, scale, delta, dqkv)
-    ref.backward(do.double().view(B, S, H, 64).permute(0, 2, 1, 3))
-    names = "qkv"
-    errs = [relerr(dqkv[:, :, i].permute(0, 2, 1, 3).float(), t.grad) for i, t in enumerate((q, k, v))]
-    report(f"attn_bwd B{B} S{S} H{H}", max(errs) < 1.5e-2, " ".join(f"d{n} {e:.2e}" for n, e in zip(names, errs)))
+    # fp64 reference, a few clips at a time (the scores of B64 S1568 H6 are 7.5 GB in fp64)
+    chunk = max(1, min(B, int(2e9 // (H * S * S * 8))))
+    num = {k: 0.0 for k in ("out", "lse", "dq", "dk", "dv")}
+    den = dict(num)
+    for b0 in range(0, B, chunk):
+        sl = slice(b0, min(B, b0 + chunk))
+        q, k, v = (qkv[sl, :, i].permute(0, 2, 1, 3).double().requires_grad_(True) for i in range(3))
+        s = (q @ k.transpose(-1, -2)) * scale
+        ref = torch.softmax(s, -1) @ v
+        ref_lse = torch.logsumexp(s, -1)
+        del s
+        ref.backward(do[sl].double().view(-1, S, H, 64).permute(0, 2, 1, 3))
+        pairs = {"out": (out[sl].float().view(-1, S, H, 64).permute(0, 2, 1, 3), ref.detach()), "lse": (lse[sl], ref_lse),
+                 "dq": (dqkv[sl, :, 0].permute(0, 2, 1, 3).float(), q.grad),
+                 "dk": (dqkv[sl, :, 1].permute(0, 2, 1, 3).float(), k.grad),
+                 "dv": (dqkv[sl, :, 2].permute(0, 2, 1, 3).float(), v.grad)}
+        for kk, (a, r) in pairs.items():
+            num[kk] += float((a.double() - r.double()).pow(2).sum())
+            den[kk] += float(r.double().pow(2).sum())
+        del q, k, v, ref, ref_lse, pairs
+    err = {kk: (num[kk] / max(den[kk], 1e-60)) ** 0.5 for kk in num}
+    report(f"attn_fwd B{B} S{S} H{H}", err["out"] < 6e-3 and err["lse"] < 1e-4, f"out {err['out']:.2e} lse {err['lse']:.2e}")
+    report(f"attn_bwd B{B} S{S} H{H}", max(err["dq"], err["dk"], err["dv"]) < 1.5e-2,
+           f"dq {err['dq']:.2e} dk {err['dk']:.2e} dv {err['dv']:.2e}")
 
 
 def run_attn():
@@ -364,6 +414,32 @@ def run_attn():
     attn_case(2, 17, 2)
     attn_case(1, 33, 1)
     attn_case(3, 159, 2)
+
+
+def run_bench_shapes():
+    """The kernel shapes of the BENCHMARK step (ViT-B/16, batch 64: M = 64 x 160 = 10240 encoder rows, 64 x 1568 =
+    100352 decoder rows, 64 x 1408 = 90112 masked rows) with the tile shapes the dispatcher picks for them on its own
+    (block_n = 0, cta_pair = 0): persistent schedulers with > 148 tiles, CTA-pair auto-selection, both accumulator
+    stages, the fused epilogues exactly as engine.py calls them."""
+    gemm_case(100352, 1536, 384, 0, 0, 0, "bias_gelu")          # decoder fc1
+    gemm_case(100352, 1536, 384, 0, 1, 0, "gelu_bwd_colsum")    # decoder fc2 dgrad x gelu'
+    gemm_case(100352, 384, 1536, 0, 0, 0, "res_f32")            # decoder fc2 (CTA pairs)
+    gemm_case(100352, 384, 384, 0, 0, 0, "res_f32")             # decoder out-proj
+    gemm_case(100352, 1152, 384, 0, 0, 0, "bias_bf16")          # decoder qkv
+    gemm_case(10240, 2304, 768, 0, 0, 0, "bias_bf16")           # encoder qkv
+    gemm_case(100352, 384, 1152, 0, 1, 0, "bias_bf16")          # decoder qkv dgrad (B MN-major)
+    gemm_case(90112, 1536, 384, 0, 0, 192, "loss_nologits")     # head + MSE
+    gemm_case(1536, 384, 100352, 1, 1, 0, "splitk", 0)          # decoder fc1 wgrad
+    gemm_case(10240, 3072, 768, 0, 0, 0, "bias_gelu")           # encoder fc1
+    gemm_case(10240, 3072, 768, 0, 1, 0, "gelu_bwd_colsum")     # encoder fc2 dgrad
+    gemm_case(10240, 768, 3072, 0, 0, 0, "res_f32")             # encoder fc2 (CTA pairs)
+    gemm_case(10240, 768, 768, 0, 0, 0, "res_f32")              # encoder out-proj
+    gemm_case(3072, 768, 10240, 1, 1, 0, "splitk", 0)           # encoder fc1 wgrad
+    attn_case(64, 160, 12)                                      # encoder attention (short-sequence kernels)
+    attn_case(64, 1568, 6)                                      # decoder attention
+    patchify_case(64, "base", 0.9)
+    ln_case(10240, 768)
+    ln_case(64 * 1408, 384, seg=(1408, 1568, 160))              # final decoder norm over the masked rows
 
 
 # ------------------------------------------------------------------------------------------------ perf probes
@@ -439,7 +515,7 @@ if __name__ == "__main__":
     for w in which:
         {"gemm00": lambda: run_gemm_major(0, 0), "gemm01": lambda: run_gemm_major(0, 1),
          "gemm10": lambda: run_gemm_major(1, 0), "gemm11": lambda: run_gemm_major(1, 1),
-         "gemmx": run_gemm_epilogues, "gemmpair": run_gemm_pair, "rows": run_rows, "patchify": run_patchify, "attn": run_attn, "perf": run_perf}[w]()
+         "gemmx": run_gemm_epilogues, "gemmpair": run_gemm_pair, "benchshapes": run_bench_shapes, "rows": run_rows, "patchify": run_patchify, "attn": run_attn, "perf": run_perf}[w]()
     torch.cuda.synchronize()
     nfail = sum(1 for _, ok in RESULTS if not ok)
     print(f"SELFTEST {len(RESULTS) - nfail}/{len(RESULTS)} passed in {time.time() - t0:.1f}s", flush=True)

@@ -167,8 +167,9 @@ def test_scaler_step_is_two_launches_and_matches_torch(opt_name):
     if opt_name == "SGD":
         for p, g in zip(pa, _grads(1, dev)):
             p.grad = g
-        fresh = torch.optim.SGD(pa, **kw)
-        sd = fresh.state_dict()          # no step yet: empty state
+        sd = torch.optim.SGD(pa, **kw).state_dict()
+        # torch's own layout for "momentum not started": the key present with value None
+        sd["state"] = {i: {"momentum_buffer": None} for i in range(len(pa))}
         ob.load_state_dict(sd)
     sa, sb = torch.amp.GradScaler("cuda", init_scale=256.0, growth_interval=2), \
         torch.amp.GradScaler("cuda", init_scale=256.0, growth_interval=2)

@@ -76,7 +76,7 @@ _SIGNATURES = {
                                         C.c_float, C.c_void_p, C.c_void_p]),
     "bvc_sgd_step": (C.c_int, [C.c_void_p, C.c_int32, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int32,
                                C.c_void_p, C.c_void_p, C.c_void_p]),
-    "bvc_adam_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
+    "bvc_adam_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double,
                                 C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "bvc_grad_nonfinite": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "bvc_jepa_apply_masks": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32,

@@ -91,20 +91,23 @@ __global__ void __launch_bounds__(256) sgd_multi_kernel(const SgdEntry* __restri
 // GradScaler must not advance it, and the host never learns whether a step was skipped.  IEEE division / square root
 // (this file is compiled without --use_fast_math).
 struct AdamHyper {
-  float lr, beta1, beta2, eps, weight_decay;
-  int decoupled;  // 1: AdamW
+  double lr, beta1, beta2, eps, weight_decay;  // torch does its scalar arithmetic on Python floats (doubles)
+  int decoupled;                               // 1: AdamW
+};
+struct AdamScalars {  // every scalar rounded to fp32 ONCE, where torch's kernels receive it
+  float w1, beta2, w2, eps, wd, decay, step_size, bc2_sqrt;
+  int decoupled;
 };
 
-__device__ __forceinline__ float adam_one(float p, float g, float& m, float& v, const AdamHyper& h, float decay,
-                                          float step_size, float bc2_sqrt) {
-  if (h.weight_decay != 0.f) {
-    if (h.decoupled) p = __fmul_rn(p, decay);
-    else g = fmaf(h.weight_decay, p, g);
+__device__ __forceinline__ float adam_one(float p, float g, float& m, float& v, const AdamScalars& h) {
+  if (h.wd != 0.f) {
+    if (h.decoupled) p = __fmul_rn(p, h.decay);
+    else g = fmaf(h.wd, p, g);
   }
-  m = fmaf(1.f - h.beta1, g - m, m);
-  v = fmaf(1.f - h.beta2, __fmul_rn(g, g), __fmul_rn(v, h.beta2));
-  const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(v), bc2_sqrt), h.eps);
-  return fmaf(-step_size, __fdiv_rn(m, denom), p);
+  m = fmaf(h.w1, g - m, m);                                       // lerp(m, g, 1 - beta1)
+  v = fmaf(h.w2, __fmul_rn(g, g), __fmul_rn(v, h.beta2));         // v * beta2 + (1 - beta2) * (g * g)
+  const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(v), h.bc2_sqrt), h.eps);
+  return fmaf(-h.step_size, __fdiv_rn(m, denom), p);
 }
 
 __global__ void __launch_bounds__(256) adam_multi_kernel(const SgdEntry* __restrict__ table,
@@ -118,9 +121,17 @@ __global__ void __launch_bounds__(256) adam_multi_kernel(const SgdEntry* __restr
   const bool first = en.m_uninit != 0;  // state buffers hold nothing yet: exp_avg = exp_avg_sq = 0
   // scalars in double like torch's Python-float arithmetic, then one rounding to fp32
   const double t = (double)*step + 1.0;
-  const double bc1 = 1.0 - pow((double)h.beta1, t), bc2 = 1.0 - pow((double)h.beta2, t);
-  const float step_size = (float)((double)h.lr / bc1), bc2_sqrt = (float)sqrt(bc2);
-  const float decay = (float)(1.0 - (double)h.lr * (double)h.weight_decay);
+  const double bc1 = 1.0 - pow(h.beta1, t), bc2 = 1.0 - pow(h.beta2, t);
+  AdamScalars sc;
+  sc.w1 = (float)(1.0 - h.beta1);
+  sc.beta2 = (float)h.beta2;
+  sc.w2 = (float)(1.0 - h.beta2);
+  sc.eps = (float)h.eps;
+  sc.wd = (float)h.weight_decay;
+  sc.decay = (float)(1.0 - h.lr * h.weight_decay);
+  sc.step_size = (float)(h.lr / bc1);
+  sc.bc2_sqrt = (float)sqrt(bc2);
+  sc.decoupled = h.decoupled;
   const bool vec_ok = ((reinterpret_cast<uintptr_t>(en.p) | reinterpret_cast<uintptr_t>(en.g) |
                         reinterpret_cast<uintptr_t>(en.m) | reinterpret_cast<uintptr_t>(vbuf) |
                         reinterpret_cast<uintptr_t>(en.shadow)) & 15) == 0;
@@ -135,10 +146,10 @@ __global__ void __launch_bounds__(256) adam_multi_kernel(const SgdEntry* __restr
       v = reinterpret_cast<const float4*>(vbuf)[i];
     }
     g.x *= inv; g.y *= inv; g.z *= inv; g.w *= inv;
-    p.x = adam_one(p.x, g.x, m.x, v.x, h, decay, step_size, bc2_sqrt);
-    p.y = adam_one(p.y, g.y, m.y, v.y, h, decay, step_size, bc2_sqrt);
-    p.z = adam_one(p.z, g.z, m.z, v.z, h, decay, step_size, bc2_sqrt);
-    p.w = adam_one(p.w, g.w, m.w, v.w, h, decay, step_size, bc2_sqrt);
+    p.x = adam_one(p.x, g.x, m.x, v.x, sc);
+    p.y = adam_one(p.y, g.y, m.y, v.y, sc);
+    p.z = adam_one(p.z, g.z, m.z, v.z, sc);
+    p.w = adam_one(p.w, g.w, m.w, v.w, sc);
     reinterpret_cast<float4*>(en.p)[i] = p;
     if (grad_scale != nullptr) reinterpret_cast<float4*>(en.g)[i] = g;
     reinterpret_cast<float4*>(en.m)[i] = m;
@@ -156,7 +167,7 @@ __global__ void __launch_bounds__(256) adam_multi_kernel(const SgdEntry* __restr
   }
   for (long long i = (nv << 2) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < en.n; i += stride) {
     float p = en.p[i], g = en.g[i] * inv, m = first ? 0.f : en.m[i], v = first ? 0.f : vbuf[i];
-    p = adam_one(p, g, m, v, h, decay, step_size, bc2_sqrt);
+    p = adam_one(p, g, m, v, sc);
     en.p[i] = p;
     if (grad_scale != nullptr) en.g[i] = g;
     en.m[i] = m;
@@ -219,11 +230,11 @@ extern "C" int bvc_sgd_step(const void* table, int32_t n_entries, float lr, floa
   return BVC_OK;
 }
 
-extern "C" int bvc_adam_step(const void* table, const void* exp_avg_sq_table, int32_t n_entries, float lr, float beta1,
-                             float beta2, float eps, float weight_decay, int32_t decoupled, float* step,
+extern "C" int bvc_adam_step(const void* table, const void* exp_avg_sq_table, int32_t n_entries, double lr, double beta1,
+                             double beta2, double eps, double weight_decay, int32_t decoupled, float* step,
                              const float* grad_scale, const float* found_inf, void* stream) {
   BVC_CHECK_ARG(table && exp_avg_sq_table && step && n_entries > 0 && n_entries <= 65535);
-  BVC_CHECK_ARG(beta1 >= 0.f && beta1 < 1.f && beta2 >= 0.f && beta2 < 1.f);
+  BVC_CHECK_ARG(beta1 >= 0.0 && beta1 < 1.0 && beta2 >= 0.0 && beta2 < 1.0);
   AdamHyper h{lr, beta1, beta2, eps, weight_decay, decoupled};
   dim3 grid(32, n_entries);
   adam_multi_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const SgdEntry*)table, (float* const*)exp_avg_sq_table, h,

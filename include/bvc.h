@@ -209,10 +209,11 @@ int bvc_sgd_step(const void* table, int32_t n_entries, float lr, float momentum,
  *   AdamW (decoupled != 0): p *= 1 - lr wd      Adam: g' += wd p
  *   m = m + (1 - beta1)(g' - m);  v = beta2 v + (1 - beta2) g' g';   t = *step + 1
  *   p -= lr / (1 - beta1^t) * m / (sqrt(v) / sqrt(1 - beta2^t) + eps)
+ * Hyper-parameters are doubles: torch derives 1 - beta, lr / (1 - beta1^t), ... in double and rounds each ONCE to fp32.
  * `step` is a device float (the group's step count before this call); a second one-thread kernel adds 1 to it after
  * the update unless *found_inf != 0, in which case the whole call is a no-op.  g, shadow, grad_scale as bvc_sgd_step. */
-int bvc_adam_step(const void* table, const void* exp_avg_sq_table, int32_t n_entries, float lr, float beta1,
-                  float beta2, float eps, float weight_decay, int32_t decoupled, float* step,
+int bvc_adam_step(const void* table, const void* exp_avg_sq_table, int32_t n_entries, double lr, double beta1,
+                  double beta2, double eps, double weight_decay, int32_t decoupled, float* step,
                   const float* grad_scale, const float* found_inf, void* stream);
 
 /* GradScaler's inf / nan check (torch._amp_foreach_non_finite_check_and_unscale_ with inv_scale 1, which re-writes

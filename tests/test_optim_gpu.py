@@ -119,7 +119,8 @@ def test_fused_sgd_refreshes_weight_copies():
 def test_fused_adam_matches_torch(cls_name, kw):
     """FusedAdamW / FusedAdam (bvc_adam_step) against torch.optim.AdamW / Adam (pretrain_videomae.py:190-193: AdamW with
     betas (0.9, 0.95)): parameters and both moments after 5 steps.  Same operation order as torch's single-tensor path,
-    scalars in double; what differs is fma contraction -- a few ulp per step: rtol 5e-6 / atol 1e-7."""
+    scalars in double; what differs is fma contraction -- a few ulp per step: rtol 5e-6 / atol 1e-7 (the moments pass
+    through zero: absolute floor of about one ulp of their typical magnitude)."""
     import bvc_b200 as bvc
     dev = torch.device("cuda:0")
     pa, pb = _params(2, dev), _params(2, dev)
@@ -134,7 +135,7 @@ def test_fused_adam_matches_torch(cls_name, kw):
     for p, q in zip(pa, pb):
         assert torch.allclose(p, q, rtol=5e-6, atol=1e-7), float((p - q).abs().max())
         for k in ("exp_avg", "exp_avg_sq"):
-            assert torch.allclose(oa.state[p][k], ob.state[q][k], rtol=5e-6, atol=1e-9), k
+            assert torch.allclose(oa.state[p][k], ob.state[q][k], rtol=5e-6, atol=1e-7), k
         assert float(ob.state[q]["step"]) == float(oa.state[p]["step"]) == 5.0
     assert set(ob.state_dict()["state"][0]) == set(oa.state_dict()["state"][0])  # checkpoints interchange
     # ... and do: torch's state loads into the fused optimizer and both continue identically

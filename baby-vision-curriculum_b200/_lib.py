@@ -64,7 +64,7 @@ _SIGNATURES = {
     "bvc_attn_fwd": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_void_p, C.c_void_p,
                                C.c_void_p]),
     "bvc_attn_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
-                               C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
+                               C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "bvc_nce_normalize_split": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_float, C.c_void_p,
                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "bvc_nce_partial_slots": (C.c_int64, [C.c_int32]),
@@ -335,11 +335,12 @@ def attn_fwd(qkv, B, S, H, scale, out, lse):
     _count()
 
 
-def attn_bwd(qkv, out, dout, lse, B, S, H, scale, delta, dqkv):
-    _cuda(qkv, out, dout, lse, delta, dqkv)
+def attn_bwd(qkv, out, dout, lse, B, S, H, scale, delta, dqkv, dq_accum=None):
+    """dq_accum: optional fp32 [B, S, H, 64] scratch; with it sequences > 160 tokens run the one-pass backward."""
+    _cuda(qkv, out, dout, lse, delta, dqkv, dq_accum)
     with _Timed("attn_bwd", 8.0 * B * H * S * S * 64, 0.0, f"B{B} S{S} H{H}"):
-        _check(load().bvc_attn_bwd(_p(qkv), _p(out), _p(dout), _p(lse), B, S, H, scale, _p(delta), _p(dqkv), _stream()),
-               "bvc_attn_bwd")
+        _check(load().bvc_attn_bwd(_p(qkv), _p(out), _p(dout), _p(lse), B, S, H, scale, _p(delta), _p(dqkv),
+                                   _p(dq_accum), _stream()), "bvc_attn_bwd")
     _count(3)
 
 

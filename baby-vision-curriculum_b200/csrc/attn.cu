@@ -847,6 +847,432 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
   }
 }
 
+
+// ================================================================================================ backward, ONE pass
+// attn_bwd1_kernel: the backward in a single pass over the (key tile, query tile) pairs -- 5 MMAs and ONE exponential
+// per score where the two-pass kernels above execute 7 and 2 (they recompute S and dP in each pass).  The CTA owns a
+// K/V tile like MODE_KV (transposed tile: rows = keys; statistics folded into the score MMAs through the augmentation
+// tile) and streams the Q / dO tiles; in addition to dV += P^T dO and dK += dS^T Q every streamed tile yields this
+// pair's contribution  dQ_i = dS K_j,  which leaves through shared memory and a TMA REDUCE (fp32 add in L2) into an
+// fp32 accumulation buffer [B, S, H, 64]; bvc_attn_bwd zero-fills that buffer before and converts it into the q slot of
+// dqkv after the kernel.
+//   dS^T (bf16) is written ONCE, to shared memory, as two 128B-swizzled [128 keys][64 queries] atoms, and read with
+//   both operand majors: K-major as the A operand of dK += dS^T Q (M = keys, K = queries) and MN-major -- transposed
+//   by the UMMA descriptor -- as the A operand of dQ = dS K (M = queries, K = keys).  P^T still goes back to TMEM.
+// TMEM (512 columns): S^T 128 | dP^T 128 | dV 64 | dK 64 | P^T (packed bf16) 64 | dQ 64.
+// Shared memory (14 tiles of 16 KB): K_j, V_j x 2 item buffers | Q_i, dO_i x 2 stages | augmentation x 2 | dS^T (2
+// atoms) | dQ staging (fp32 [128][32] x 2 column halves).
+// Per streamed tile the compute warps: read S^T / dP^T (TMEM), exp + dS math, drain the PREVIOUS tile's dQ accumulator
+// into the staging buffer (the store warp reduces it into global memory), write P^T (TMEM) and dS^T (smem).
+constexpr int kB1Stages = 2;
+constexpr int kB1Smem = kTileBytes * 14 + 256;
+static_assert(kB1Smem <= 232448, "single-pass backward: shared memory");
+
+__device__ __forceinline__ void tma_reduce_add_4d(const CUtensorMap* m, const void* smem_src, int c0, int c1, int c2,
+                                                  int c3) {
+  asm volatile("cp.reduce.async.bulk.tensor.4d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+
+__global__ void __launch_bounds__(kBwdThreads, 1)
+attn_bwd1_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
+                 const __grid_constant__ CUtensorMap tm_dqkv, const __grid_constant__ CUtensorMap tm_dq,
+                 const float* __restrict__ lse, const float* __restrict__ delta, int S, int H, int n_work, float scale) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sR = smem;                                   // [2 buffers][K_j | V_j]
+  uint8_t* sX = smem + 4 * kTileBytes;                  // [stages] Q_i
+  uint8_t* sY = smem + (4 + kB1Stages) * kTileBytes;    // [stages] dO_i
+  uint8_t* sAug = smem + (4 + 2 * kB1Stages) * kTileBytes;      // [2]
+  uint8_t* sDS = smem + (6 + 2 * kB1Stages) * kTileBytes;       // dS^T: 2 atoms of [128 keys][64 queries]
+  uint8_t* sDQ = smem + (8 + 2 * kB1Stages) * kTileBytes;       // dQ staging: 2 halves of fp32 [128 queries][32]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (10 + 2 * kB1Stages) * kTileBytes);
+  uint64_t* r_full = bars + 0;                   // [2]
+  uint64_t* r_empty = bars + 2;                  // [2]
+  uint64_t* st_full = bars + 4;                  // [stages]
+  uint64_t* st_empty = bars + 4 + kB1Stages;     // [stages]
+  uint64_t* sdp_full = bars + 4 + 2 * kB1Stages;
+  uint64_t* sdp_free = sdp_full + 1;
+  uint64_t* pds_full = sdp_full + 2;             // compute -> MMA: P^T in TMEM, dS^T in smem, previous dQ drained
+  uint64_t* acc_done = sdp_full + 3;             // MMA (commit) -> compute: dV / dK / dQ MMAs of a tile complete
+  uint64_t* aug_full = sdp_full + 4;             // [2]
+  uint64_t* aug_empty = sdp_full + 6;            // [2]
+  uint64_t* epi_full = sdp_full + 8;             // compute -> store warp: an item's dV / dK are staged
+  uint64_t* dq_staged = sdp_full + 9;            // compute -> store warp: a tile's dQ contribution is staged
+  uint64_t* dq_stage_free = sdp_full + 10;       // store warp -> compute: the TMA reduce has read the staging buffer
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sdp_full + 11);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_it = (S + kTile - 1) / kTile;
+  const int n_my = (n_work - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int n_glob = n_my * n_it;
+  auto item_tile = [&](int k) { return ((int)blockIdx.x + k * (int)gridDim.x) % n_it; };
+  auto item_bh = [&](int k) { return ((int)blockIdx.x + k * (int)gridDim.x) / n_it; };  // = b * H + h
+
+  if (threadIdx.x == 0) {
+    if ((smem_u32(smem) & 1023u) != 0) __trap();
+    tma_prefetch_desc(&tm_qkv);
+    tma_prefetch_desc(&tm_do);
+    tma_prefetch_desc(&tm_dqkv);
+    tma_prefetch_desc(&tm_dq);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&r_full[i], 1);
+      mbar_init(&r_empty[i], 1);
+      mbar_init(&aug_full[i], 1);
+      mbar_init(&aug_empty[i], 1);
+    }
+    for (int i = 0; i < kB1Stages; ++i) {
+      mbar_init(&st_full[i], 1);
+      mbar_init(&st_empty[i], 1);
+    }
+    mbar_init(sdp_full, 1);
+    mbar_init(sdp_free, 8);
+    mbar_init(pds_full, 8);
+    mbar_init(acc_done, 1);
+    mbar_init(epi_full, 8);
+    mbar_init(dq_staged, 8);
+    mbar_init(dq_stage_free, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tS = tmem_base, tDP = tmem_base + 128, tDV = tmem_base + 256, tDK = tmem_base + 320;
+  const uint32_t tP = tmem_base + 384, tDQ = tmem_base + 448;
+
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kBwdRegsCtl));
+    if (warp == 0) {
+      if (lane == 0) {
+        int g = 0;
+        for (int k = 0; k < n_my; ++k) {
+          const int own0 = item_tile(k) * kTile, bh = item_bh(k), h = bh % H, b = bh / H;
+          uint8_t* r0 = sR + (k & 1) * 2 * kTileBytes;
+          mbar_wait(&r_empty[k & 1], ((uint32_t)(k >> 1) & 1u) ^ 1u);
+          mbar_expect_tx(&r_full[k & 1], 2 * kTileBytes);
+          tma_load_4d(r0, &tm_qkv, &r_full[k & 1], 0, H + h, own0, b);
+          tma_load_4d(r0 + kTileBytes, &tm_qkv, &r_full[k & 1], 0, 2 * H + h, own0, b);
+          for (int i = 0; i < n_it; ++i, ++g) {
+            const int st = g % kB1Stages;
+            mbar_wait(&st_empty[st], ((uint32_t)(g / kB1Stages) & 1u) ^ 1u);
+            mbar_expect_tx(&st_full[st], 2 * kTileBytes);
+            tma_load_4d(sX + st * kTileBytes, &tm_qkv, &st_full[st], 0, h, i * kTile, b);
+            tma_load_4d(sY + st * kTileBytes, &tm_do, &st_full[st], 0, h, i * kTile, b);
+          }
+        }
+      }
+    } else if (warp == 1) {
+      constexpr uint32_t idesc_acc = umma_idesc_bf16(64, 0, 1, 128);  // A K-major (TMEM or smem), B MN-major, N = 64
+      constexpr uint32_t idesc_dq = umma_idesc_bf16(64, 1, 1, 128);   // A = dS^T read MN-major, B = K_j MN-major
+      auto valid16 = [&](int i) { return min(kTile, (S - i * kTile + 15) & ~15); };
+      auto issue_s_dp = [&](int k, int i, int st, int gg) {
+        const uint64_t dAug = desc_k(smem_u32(sAug + (gg & 1) * kTileBytes), 0);
+        const uint32_t idesc_s = umma_idesc_bf16(valid16(i), 0, 0, 128);
+        const uint32_t aR = smem_u32(sR + (k & 1) * 2 * kTileBytes);
+        const uint64_t dR0 = desc_k(aR, 0), dR1 = desc_k(aR + kTileBytes, 0);
+        const uint64_t dX = desc_k(smem_u32(sX + st * kTileBytes), 0), dY = desc_k(smem_u32(sY + st * kTileBytes), 0);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) umma_bf16_ss(tS, dR0 + 2 * kk, dX + 2 * kk, idesc_s, kk > 0);
+        umma_bf16_ss(tS, dAug, dAug + 2, idesc_s, 1);       // S^T - lse_q / scale
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) umma_bf16_ss(tDP, dR1 + 2 * kk, dY + 2 * kk, idesc_s, kk > 0);
+        umma_bf16_ss(tDP, dAug, dAug + 4, idesc_s, 1);      // dP^T - delta_q
+        umma_commit(&aug_empty[gg & 1]);
+      };
+      if (n_glob > 0) {
+        mbar_wait(&r_full[0], 0);
+        mbar_wait(&st_full[0], 0);
+        mbar_wait(&aug_full[0], 0);
+        tc_fence_after();
+        if (elect_one()) {
+          issue_s_dp(0, 0, 0, 0);
+          umma_commit(sdp_full);
+        }
+        __syncwarp();
+      }
+      int k = 0, i = 0;
+      for (int g = 0; g < n_glob; ++g) {
+        int k1 = k, i1 = i + 1;
+        if (i1 == n_it) {
+          i1 = 0;
+          ++k1;
+        }
+        if (lane == 0) BVC_TR(2, g, 0);
+        if (g + 1 < n_glob) {
+          const int st1 = (g + 1) % kB1Stages;
+          if (i1 == 0) mbar_wait(&r_full[k1 & 1], (uint32_t)(k1 >> 1) & 1u);
+          mbar_wait(&st_full[st1], (uint32_t)((g + 1) / kB1Stages) & 1u);
+          mbar_wait(&aug_full[(g + 1) & 1], (uint32_t)((g + 1) >> 1) & 1u);
+          if (lane == 0) BVC_TR(2, g, 1);
+          mbar_wait(sdp_free, (uint32_t)g & 1u);
+          if (lane == 0) BVC_TR(2, g, 2);
+          tc_fence_after();
+          if (elect_one()) {
+            issue_s_dp(k1, i1, st1, g + 1);
+            umma_commit(sdp_full);
+          }
+          __syncwarp();
+        }
+        if (lane == 0) BVC_TR(2, g, 3);
+        mbar_wait(pds_full, (uint32_t)g & 1u);
+        if (lane == 0) BVC_TR(2, g, 4);
+        tc_fence_after();
+        const int cst = g % kB1Stages;
+        const int ksteps = valid16(i) >> 4;               // queries of the streamed tile: reduction of dV / dK
+        const int ksteps_kv = valid16(item_tile(k)) >> 4; // keys of the owned tile: reduction of dQ
+        if (elect_one()) {
+          const uint64_t dX = desc_mn(smem_u32(sX + cst * kTileBytes), 0, 8192);   // Q_i : n = d, k = query
+          const uint64_t dY = desc_mn(smem_u32(sY + cst * kTileBytes), 0, 8192);   // dO_i
+          const uint64_t dKj = desc_mn(smem_u32(sR + (k & 1) * 2 * kTileBytes), 0, 8192);  // K_j : n = d, k = key
+          const uint32_t ds_base = smem_u32(sDS);
+          const uint32_t acc0 = i > 0;
+          // dV[key, d] += P^T dO   (A = P^T from TMEM)
+          for (int kk = 0; kk < ksteps; ++kk) umma_bf16_ts(tDV, tP + kk * 8, dY + 128 * kk, idesc_acc, acc0 | (kk > 0));
+          // dK[key, d] += dS^T Q   (A = dS^T from smem, K-major: queries 16 kk .. inside atom kk / 4)
+          for (int kk = 0; kk < ksteps; ++kk)
+            umma_bf16_ss(tDK, desc_k(ds_base + (kk >> 2) * kTileBytes, kk & 3), dX + 128 * kk, idesc_acc, acc0 | (kk > 0));
+          // dQ_i[query, d] = dS K_j (A = dS^T read MN-major: m = query, k = key; 16 keys = 2048 bytes per k-step, the
+          // second 64 queries are the second atom)
+          for (int kk = 0; kk < ksteps_kv; ++kk)
+            umma_bf16_ss(tDQ, umma_smem_desc(ds_base + kk * 2048, 1024, kTileBytes), dKj + 128 * kk, idesc_dq, kk > 0);
+          umma_commit(acc_done);
+          umma_commit(&st_empty[cst]);
+        }
+        __syncwarp();
+        if (lane == 0) BVC_TR(2, g, 5);
+        k = k1;
+        i = i1;
+      }
+    } else if (warp == 2) {
+      // statistics warp: as in attn_bwd_kernel<1>
+      const uint4 ones = make_uint4(pack_bf16x2(1.f, 1.f), pack_bf16x2(1.f, 0.f), 0u, 0u);
+      const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+      for (int r = lane; r < 2 * kTile; r += 32) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          if (c != 2 && c != 4) *reinterpret_cast<uint4*>(sAug + r * 128 + ((c ^ (r & 7)) << 4)) = c == 0 ? ones : zero;
+      }
+      float cur[8], nxt[8];
+      auto load8 = [&](int kk, int ii, float (&v)[8]) {
+        const float* lb = lse + (long long)item_bh(kk) * S;
+        const float* db = delta + (long long)item_bh(kk) * S;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int qg = min(ii * kTile + lane * 4 + j, S - 1);
+          v[j] = __ldg(lb + qg);
+          v[4 + j] = __ldg(db + qg);
+        }
+      };
+      int k = 0, i = 0;
+      if (n_glob > 0) load8(0, 0, cur);
+      for (int g = 0; g < n_glob; ++g) {
+        int k1 = k, i1 = i + 1;
+        if (i1 == n_it) {
+          i1 = 0;
+          ++k1;
+        }
+        if (g + 1 < n_glob) load8(k1, i1, nxt);
+        mbar_wait(&aug_empty[g & 1], ((uint32_t)(g >> 1) & 1u) ^ 1u);
+        uint8_t* tile = sAug + (g & 1) * kTileBytes;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int r = lane * 4 + (j & 3);
+          const float v = j < 4 ? -cur[j] / scale : -cur[j];
+          const float hi = __bfloat162float(__float2bfloat16_rn(v));
+          const float r1 = v - hi;
+          const float mid = __bfloat162float(__float2bfloat16_rn(r1));
+          const float lo = r1 - mid;
+          *reinterpret_cast<uint4*>(tile + r * 128 + (((j < 4 ? 2 : 4) ^ (r & 7)) << 4)) =
+              make_uint4(pack_bf16x2(hi, mid), pack_bf16x2(lo, 0.f), 0u, 0u);
+        }
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&aug_full[g & 1]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) cur[j] = nxt[j];
+        k = k1;
+        i = i1;
+      }
+    } else {
+      // store warp: per streamed tile (from the second on) the previous tile's dQ contribution -> TMA reduce-add into
+      // the fp32 accumulation buffer; per item dV / dK -> TMA stores.  Same event order as the compute warps produce.
+      int n_dq = 0;
+      auto reduce_dq = [&](int gp) {
+        mbar_wait(dq_staged, (uint32_t)n_dq & 1u);
+        if (lane == 0) {
+          const int kp = gp / n_it, ip = gp % n_it, bh = item_bh(kp), h = bh % H, b = bh / H;
+          tma_reduce_add_4d(&tm_dq, sDQ, 0, h, ip * kTile, b);
+          tma_reduce_add_4d(&tm_dq, sDQ + kTileBytes, 32, h, ip * kTile, b);
+          tma_store_commit();
+          tma_store_wait_read0();
+          mbar_arrive(dq_stage_free);
+        }
+        __syncwarp();
+        ++n_dq;
+      };
+      int g = 0;
+      for (int k = 0; k < n_my; ++k) {
+        const int own0 = item_tile(k) * kTile, bh = item_bh(k), h = bh % H, b = bh / H;
+        uint8_t* stage = sR + (k & 1) * 2 * kTileBytes;
+        for (int i = 0; i < n_it; ++i, ++g)
+          if (g > 0) reduce_dq(g - 1);
+        mbar_wait(epi_full, (uint32_t)k & 1u);
+        if (lane == 0) {
+          tma_store_4d(&tm_dqkv, stage, 0, 2 * H + h, own0, b);               // dV
+          tma_store_4d(&tm_dqkv, stage + kTileBytes, 0, H + h, own0, b);      // dK
+          tma_store_commit();
+          tma_store_wait_read0();
+          mbar_arrive(&r_empty[k & 1]);
+        }
+        __syncwarp();
+      }
+      if (n_glob > 0) reduce_dq(n_glob - 1);
+      if (lane == 0) tma_store_wait0();
+    }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kBwdRegsCompute));
+    const int e = warp - 4;
+    const int q4 = warp & 3;
+    const int half = e >> 2;
+    const int row = q4 * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(q4 * 32) << 16;
+    const float c_log2 = scale * kLog2e;
+    const uint64_t cl2 = pack2(c_log2, c_log2), sc2 = pack2(scale, scale);
+    const uint32_t ds_row = smem_u32(sDS) + (uint32_t)half * kTileBytes + (uint32_t)row * 128;   // this thread's dS^T row
+    const uint32_t dq_row = smem_u32(sDQ) + (uint32_t)half * kTileBytes + (uint32_t)row * 128;   // ... dQ staging row
+    const int sw = row & 7;
+    int n_dq = 0;
+    // drain the dQ accumulator of the previous tile (its MMAs are complete: acc_done) into the staging buffer
+    auto drain_dq = [&]() {
+      uint32_t qv[32];
+      tmem_ld_32x32b_x32(tDQ + lane_base + half * 32, qv);
+      tmem_ld_wait_pin(qv);
+      if (n_dq > 0) mbar_wait(dq_stage_free, (uint32_t)(n_dq - 1) & 1u);
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+        sts_u4(dq_row + ((c ^ sw) << 4), qv[4 * c], qv[4 * c + 1], qv[4 * c + 2], qv[4 * c + 3]);
+      tc_fence_before();
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(dq_staged);
+      ++n_dq;
+    };
+    int g = 0;
+    for (int k = 0; k < n_my; ++k) {
+      for (int i = 0; i < n_it; ++i, ++g) {
+        const bool tr = lane == 0 && q4 == 0;
+        if (tr) BVC_TR(half, g, 0);
+        mbar_wait(sdp_full, (uint32_t)g & 1u);
+        if (tr) BVC_TR(half, g, 1);
+        tc_fence_after();
+        uint32_t sv[2][32], dv[2][32];
+#pragma unroll
+        for (int c = 0; c < 2; ++c) tmem_ld_32x32b_x32(tS + lane_base + half * 64 + c * 32, sv[c]);
+#pragma unroll
+        for (int c = 0; c < 2; ++c) tmem_ld_32x32b_x32(tDP + lane_base + half * 64 + c * 32, dv[c]);
+        tmem_ld_wait_pin(sv[0]);
+        tmem_ld_wait_pin(sv[1]);
+        tmem_ld_wait_pin(dv[0]);
+        tmem_ld_wait_pin(dv[1]);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(sdp_free);
+        if (tr) BVC_TR(half, g, 2);
+        uint32_t pk[32], dk[32];
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            const uint64_t s2 = pack2(__uint_as_float(sv[c][j]), __uint_as_float(sv[c][j + 1]));
+            const uint64_t p2 = pack2(__uint_as_float(dv[c][j]), __uint_as_float(dv[c][j + 1]));
+            const uint64_t e2 = exp2_mufu2(fmul2(s2, cl2));   // P = exp2((S - lse/scale) * scale * log2e)
+            float p0, p1, d0, d1;
+            unpack2(e2, p0, p1);
+            unpack2(fmul2(e2, fmul2(p2, sc2)), d0, d1);       // dS = P * (dP - delta) * scale
+            pk[c * 16 + (j >> 1)] = pack_bf16x2(p0, p1);
+            dk[c * 16 + (j >> 1)] = pack_bf16x2(d0, d1);
+          }
+        if (tr) BVC_TR(half, g, 3);
+        if (g > 0) {
+          mbar_wait(acc_done, (uint32_t)(g - 1) & 1u);  // previous tile: P^T / dS^T consumed, dQ accumulator complete
+          tc_fence_after();
+          drain_dq();
+        }
+        if (tr) BVC_TR(half, g, 4);
+        tmem_st_32x32b_x32(tP + lane_base + half * 32, pk);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) sts_u4(ds_row + ((c ^ sw) << 4), dk[4 * c], dk[4 * c + 1], dk[4 * c + 2], dk[4 * c + 3]);
+        tmem_st_wait();
+        tc_fence_before();
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(pds_full);
+        if (tr) BVC_TR(half, g, 5);
+      }
+      // item epilogue: dV / dK -> bf16 -> the finished item's resident-tile buffer -> TMA stores (store warp)
+      mbar_wait(acc_done, (uint32_t)(g - 1) & 1u);
+      if (lane == 0 && q4 == 0) BVC_TR(half, g - 1, 6);
+      tc_fence_after();
+      uint8_t* stage = sR + (k & 1) * 2 * kTileBytes;
+      auto stage32 = [&](uint32_t tacc, uint8_t* dst_tile) {
+        uint32_t ov[32];
+        tmem_ld_32x32b_x32(tacc + lane_base + half * 32, ov);
+        tmem_ld_wait();
+#pragma unroll
+        for (int gq = 0; gq < 4; ++gq) {
+          uint4 o4;
+          o4.x = pack_bf16x2(__uint_as_float(ov[gq * 8 + 0]), __uint_as_float(ov[gq * 8 + 1]));
+          o4.y = pack_bf16x2(__uint_as_float(ov[gq * 8 + 2]), __uint_as_float(ov[gq * 8 + 3]));
+          o4.z = pack_bf16x2(__uint_as_float(ov[gq * 8 + 4]), __uint_as_float(ov[gq * 8 + 5]));
+          o4.w = pack_bf16x2(__uint_as_float(ov[gq * 8 + 6]), __uint_as_float(ov[gq * 8 + 7]));
+          *reinterpret_cast<uint4*>(dst_tile + row * 128 + (((half * 4 + gq) ^ (row & 7)) << 4)) = o4;
+        }
+      };
+      stage32(tDV, stage);
+      stage32(tDK, stage + kTileBytes);
+      tc_fence_before();
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(epi_full);
+      if (lane == 0 && q4 == 0) BVC_TR(half, g - 1, 7);
+    }
+    // the last tile's dQ contribution (acc_done of the last tile was awaited by the last item epilogue)
+    if (n_glob > 0) {
+      tc_fence_after();
+      drain_dq();
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// dqkv[b, s, 0, h, :] = bf16(dq_accum[b, s, h, :])   (8 floats -> one 16-byte store per thread step)
+__global__ void __launch_bounds__(256) attn_dq_convert_kernel(const float* __restrict__ acc, bf16* __restrict__ dqkv,
+                                                              long long n8, int H) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += stride) {
+    const float4 a = ldv_f4(acc + i * 8), b = ldv_f4(acc + i * 8 + 4);
+    const long long row = i >> 3;            // (b * S + s) * H + h
+    const int c8 = (int)(i & 7);
+    const long long bs = row / H;
+    const int h = (int)(row - bs * H);
+    uint4 o;
+    o.x = pack_bf16x2(a.x, a.y);
+    o.y = pack_bf16x2(a.z, a.w);
+    o.z = pack_bf16x2(b.x, b.y);
+    o.w = pack_bf16x2(b.z, b.w);
+    *reinterpret_cast<uint4*>(dqkv + (bs * 3 * H + h) * 64 + c8 * 8) = o;
+  }
+}
+
 }  // namespace bvc
 
 using namespace bvc;
@@ -888,12 +1314,13 @@ extern "C" int bvc_attn_fwd(const void* qkv, int32_t B, int32_t S, int32_t H, fl
 }
 
 extern "C" int bvc_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, int32_t B, int32_t S,
-                            int32_t H, float scale, float* delta, void* dqkv, void* stream) {
+                            int32_t H, float scale, float* delta, void* dqkv, float* dq_accum, void* stream) {
   BVC_CHECK_ARG(qkv && out && dout && lse && delta && dqkv && B > 0 && S > 0 && H > 0);
   BVC_CHECK_ARG((((uintptr_t)qkv) & 15) == 0 && (((uintptr_t)dout) & 15) == 0 && (((uintptr_t)dqkv) & 15) == 0);
   static const bool attr_ok = !(cudaFuncSetAttribute(attn_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem) != cudaSuccess ||
-        cudaFuncSetAttribute(attn_bwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem) != cudaSuccess);  // once, thread-safe (C++11 static initialisation)
-  if (!attr_ok) return BVC_ERR_LAUNCH;
+        cudaFuncSetAttribute(attn_bwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem) != cudaSuccess ||
+        cudaFuncSetAttribute(attn_bwd1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kB1Smem) != cudaSuccess);
+  if (!attr_ok) return BVC_ERR_LAUNCH;  // once, thread-safe (C++11 static initialisation)
   cudaStream_t st = (cudaStream_t)stream;
   const long long rows = (long long)B * S * H;
   long long g = (rows + 63) / 64;
@@ -917,6 +1344,32 @@ extern "C" int bvc_attn_bwd(const void* qkv, const void* out, const void* dout, 
   CUtensorMap tdq;
   rc = make_head_tmap(&tdq, dqkv, 3 * H, S, B);
   if (rc) return rc;
+  // general sequences: ONE pass (attn_bwd1_kernel) when the caller provides the fp32 dQ accumulation workspace
+  // [B, S, H, 64]; BVC_ATTN_BWD1=0 (or a null workspace) selects the two-pass kernels (A/B measurements)
+  static const bool one_pass = []() {
+    const char* e = getenv("BVC_ATTN_BWD1");
+    return !(e && e[0] == '0');
+  }();
+  if (dq_accum != nullptr && one_pass) {
+    BVC_CHECK_ARG((((uintptr_t)dq_accum) & 15) == 0);
+    CUtensorMap tacc;
+    {
+      const uint64_t dims[4] = {64, (uint64_t)H, (uint64_t)S, (uint64_t)B};
+      const uint64_t strides[3] = {256, (uint64_t)H * 256, (uint64_t)S * H * 256};
+      const uint32_t box[4] = {32, 1, 128, 1};
+      rc = make_tmap(&tacc, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, dq_accum, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+      if (rc) return rc;
+    }
+    if (cudaMemsetAsync(dq_accum, 0, (size_t)rows * 64 * sizeof(float), st) != cudaSuccess) return BVC_ERR_LAUNCH;
+    attn_bwd1_kernel<<<grid, kBwdThreads, kB1Smem, st>>>(tq, td, tdq, tacc, lse, delta, S, H, (int)n_work, scale);
+    BVC_CHECK_LAUNCH();
+    const long long n8 = rows * 8;
+    long long gc = (n8 + 255) / 256;
+    if (gc > (long long)num_sms() * 16) gc = (long long)num_sms() * 16;
+    attn_dq_convert_kernel<<<(int)gc, 256, 0, st>>>(dq_accum, (bf16*)dqkv, n8, H);
+    BVC_CHECK_LAUNCH();
+    return BVC_OK;
+  }
   attn_bwd_kernel<1><<<grid, kBwdThreads, kBwdSmem, st>>>(tq, td, tdq, lse, delta, S, H, (int)n_work, scale);
   BVC_CHECK_LAUNCH();
   attn_bwd_kernel<0><<<grid, kBwdThreads, kBwdSmem, st>>>(tq, td, tdq, lse, delta, S, H, (int)n_work, scale);

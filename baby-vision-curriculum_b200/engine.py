@@ -344,7 +344,10 @@ def _block_bwd(ctx, dxo):
     # attention core
     dqkv = _empty((M, 3 * d), BF16, dev)
     delta = _empty((B, H, S), F32, dev)
-    L.attn_bwd(qkv, attn, d_attn, lse, B, S, H, scale, delta, dqkv)
+    # long sequences (the decoder's 1568 tokens): one-pass backward, dQ contributions reduced into an fp32 scratch
+    dq_acc = _empty((B, S, H, 64), F32, dev) if S > 160 else None
+    L.attn_bwd(qkv, attn, d_attn, lse, B, S, H, scale, delta, dqkv, dq_acc)
+    del dq_acc
     # fused QKV projection
     d_u1 = _empty((M, d), BF16, dev)
     L.gemm(dqkv, wqkv, M, d, 3 * d, b_mn=True, ldb=d, out_bf16=d_u1)

@@ -28,7 +28,7 @@ extern "C" {
 #define BVC_ERR_ARG (-1)
 #define BVC_ERR_DRIVER (-2)
 #define BVC_ERR_LAUNCH (-3)
-#define BVC_ABI_VERSION 13
+#define BVC_ABI_VERSION 14
 
 /* library / build info: returns BVC_ABI_VERSION (bumped when a signature changes) */
 int bvc_abi_version(void);
@@ -181,11 +181,15 @@ int bvc_decoder_mask_rows(float* x, const float* mask_token, const float* pos, c
  *   out  bf16 [B, S, H*64];  lse fp32 [B, H, S] (natural-log sum-exp of the scaled scores)
  * Backward: dqkv bf16 [B, S, 3, H, 64] from dout bf16 [B, S, H*64], recomputing P from lse.
  *   delta fp32 [B, H, S] is scratch (rowsum(dO * O)).
+ *   dq_accum fp32 [B, S, H, 64] is optional scratch: with it, sequences longer than 160 run the ONE-pass backward
+ *   (5 MMAs and one exponential per score; each (key tile, query tile) pair's dQ contribution is added into dq_accum
+ *   by TMA reduce and converted into dqkv's q slot afterwards); with NULL the two-pass kernels run (no atomics,
+ *   7 MMAs and two exponentials per score).  The call zero-fills dq_accum itself.
  * ------------------------------------------------------------------------------------------------------ */
 int bvc_attn_fwd(const void* qkv, int32_t B, int32_t S, int32_t H, float scale, void* out, float* lse,
                  void* stream);
 int bvc_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, int32_t B, int32_t S,
-                 int32_t H, float scale, float* delta, void* dqkv, void* stream);
+                 int32_t H, float scale, float* delta, void* dqkv, float* dq_accum, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------
  * Optimizer step (pretrain_videomae.py:187-197 torch.optim.SGD(nesterov) under GradScaler :312-314) as one

@@ -40,3 +40,7 @@ b = t(lambda: L.attn_bwd(qkv, out, do, lse, B, S, H, scale, delta, dqkv))
 fl = 4.0 * B * H * S * S * 64
 print(f"PROBE attn B{B} S{S} H{H}: fwd {f*1e3:.1f} us {fl/f/1e9:.0f} TFLOP/s | bwd {b*1e3:.1f} us {2*fl/b/1e9:.0f} TFLOP/s (credited 2x fwd)",
       flush=True)
+if S > 160:  # with the fp32 dQ workspace: the one-pass kernel (memset + kernel + convert)
+    acc = torch.empty(B, S, H, 64, device=dev)
+    b1 = t(lambda: L.attn_bwd(qkv, out, do, lse, B, S, H, scale, delta, dqkv, acc))
+    print(f"PROBE attn B{B} S{S} H{H}: bwd one-pass {b1*1e3:.1f} us {2*fl/b1/1e9:.0f} TFLOP/s (credited 2x fwd)", flush=True)

@@ -371,9 +371,15 @@ def attn_case(B, S, H, seed=0):
     dqkv = torch.zeros_like(qkv)
     delta = torch.zeros(B, H, S, device=dev)
     L.attn_bwd(qkv, out, do, lse, B, S, H, scale, delta, dqkv)
+    # S > 160: the same call with the fp32 dQ workspace runs the ONE-pass kernel (attn_bwd1); poisoned workspace
+    dqkv1 = None
+    if S > 160:
+        dqkv1 = torch.full_like(qkv, float("nan"))
+        L.attn_bwd(qkv, out, do, lse, B, S, H, scale, torch.zeros(B, H, S, device=dev), dqkv1,
+                   torch.full((B, S, H, 64), float("nan"), device=dev))
     # fp64 reference, a few clips at a time (the scores of B64 S1568 H6 are 7.5 GB in fp64)
     chunk = max(1, min(B, int(2e9 // (H * S * S * 8))))
-    num = {k: 0.0 for k in ("out", "lse", "dq", "dk", "dv")}
+    num = {k: 0.0 for k in ("out", "lse", "dq", "dk", "dv") + (("dq1", "dk1", "dv1") if dqkv1 is not None else ())}
     den = dict(num)
     for b0 in range(0, B, chunk):
         sl = slice(b0, min(B, b0 + chunk))
@@ -387,6 +393,9 @@ def attn_case(B, S, H, seed=0):
                  "dq": (dqkv[sl, :, 0].permute(0, 2, 1, 3).float(), q.grad),
                  "dk": (dqkv[sl, :, 1].permute(0, 2, 1, 3).float(), k.grad),
                  "dv": (dqkv[sl, :, 2].permute(0, 2, 1, 3).float(), v.grad)}
+        if dqkv1 is not None:
+            for i_, n_ in enumerate(("dq1", "dk1", "dv1")):
+                pairs[n_] = (dqkv1[sl, :, i_].permute(0, 2, 1, 3).float(), (q, k, v)[i_].grad)
         for kk, (a, r) in pairs.items():
             num[kk] += float((a.double() - r.double()).pow(2).sum())
             den[kk] += float(r.double().pow(2).sum())
@@ -395,6 +404,9 @@ def attn_case(B, S, H, seed=0):
     report(f"attn_fwd B{B} S{S} H{H}", err["out"] < 6e-3 and err["lse"] < 1e-4, f"out {err['out']:.2e} lse {err['lse']:.2e}")
     report(f"attn_bwd B{B} S{S} H{H}", max(err["dq"], err["dk"], err["dv"]) < 1.5e-2,
            f"dq {err['dq']:.2e} dk {err['dk']:.2e} dv {err['dv']:.2e}")
+    if dqkv1 is not None:
+        report(f"attn_bwd one-pass B{B} S{S} H{H}", max(err["dq1"], err["dk1"], err["dv1"]) < 1.5e-2,
+               f"dq {err['dq1']:.2e} dk {err['dk1']:.2e} dv {err['dv1']:.2e}")
 
 
 def run_attn():

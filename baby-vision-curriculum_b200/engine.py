@@ -344,8 +344,13 @@ def _block_bwd(ctx, dxo):
     # attention core
     dqkv = _empty((M, 3 * d), BF16, dev)
     delta = _empty((B, H, S), F32, dev)
-    # long sequences (the decoder's 1568 tokens): one-pass backward, dQ contributions reduced into an fp32 scratch
-    dq_acc = _empty((B, S, H, 64), F32, dev) if S > 160 else None
+    # long sequences (the decoder's 1568 tokens): one-pass backward, dQ contributions reduced into an fp32 scratch.
+    # The reduction order of those fp32 adds (TMA reduce, L2 atomics) varies from run to run -- like torch's own flash
+    # attention backward -- so two backward passes agree to ~2e-5 (global rel-L2; up to ~4e-4 on a single deep tensor,
+    # bf16 roundings downstream amplify last-bit differences) instead of bit for bit.  Under
+    # torch.use_deterministic_algorithms(True) (or BVC_ATTN_BWD1=0) the deterministic two-pass kernels run instead.
+    one_pass = S > 160 and not torch.are_deterministic_algorithms_enabled()
+    dq_acc = _empty((B, S, H, 64), F32, dev) if one_pass else None
     L.attn_bwd(qkv, attn, d_attn, lse, B, S, H, scale, delta, dqkv, dq_acc)
     del dq_acc
     # fused QKV projection

@@ -217,6 +217,28 @@ def hf_gpu_baseline(c, B, dev, clips, masks, steps=6, warm=3):
 
 
 # ====================================================================================================== our arm
+def bind_to_gpu_numa(local):
+    """Multi-GPU runs: pin this rank's threads to the CPUs NVML reports as local to its GPU BEFORE the pinned staging
+    buffers are allocated (first touch places them on that socket), so the per-step H2D copies of the 8 ranks do not all
+    cross the inter-socket link.  Returns the number of CPUs bound to, or None when NVML / the affinity call is
+    unavailable (nothing changes then)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(int(os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",")[local])
+                                              if os.environ.get("CUDA_VISIBLE_DEVICES") else local)
+        n_words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
+        cpus = {64 * w + b for w, word in enumerate(mask) for b in range(64) if (int(word) >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return len(cpus)
+    except Exception:
+        return None
+
+
 def run_ours(args):
     import torch.distributed as dist
     import bvc_b200 as bvc
@@ -227,6 +249,7 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = bind_to_gpu_numa(local) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     c = CONFIGS[args.config]
@@ -493,7 +516,8 @@ def run_ours(args):
             "config": {"workload": f"VideoMAE ViT-{args.config[0].upper()}/16 pretraining step (fwd+loss+bwd+DDP allreduce+"
                                    f"GradScaler/{'bvc.FusedSGD' if args.optimizer == 'fused' else 'torch.optim.SGD'}-nesterov), 16x224x224 clips, "
                                    f"tube mask 0.9, batch {B}/GPU",
-                       "global_batch": clips, "parallelism": f"dp{world}" + (f" ({args.ddp} DDP)" if world > 1 else ""), "l2": "inputs larger than L2 "
+                       "global_batch": clips, "parallelism": f"dp{world}" + (f" ({args.ddp} DDP)" if world > 1 else ""),
+                       "numa_cpus_bound_rank0": numa, "l2": "inputs larger than L2 "
                        "(616 MB clip batch per step, alternating between two resident batches)"},
             "ms_per_step_profiled": ms_prof / args.steps,
             "model_tflops_per_gpu": step_flops / (ms / args.steps) / 1e9,

@@ -123,7 +123,7 @@ class _StandIn(torch.nn.Module):
         return _StageFn.apply(x, self.w, self.b, self)
 
 
-def _ddp_worker(rank, world, port, out):
+def _ddp_worker(rank, world, port, out, cap):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     sys.path.insert(0, ROOT)
@@ -132,7 +132,8 @@ def _ddp_worker(rank, world, port, out):
     with torch.no_grad():
         m.w.fill_(float(rank + 5))  # replicas differ before wrapping: rank 0's values must win
     x = torch.arange(4.0) + 10 * rank
-    ddp = bvc.DistributedDataParallel(m, device_ids=None, output_device=None, find_unused_parameters=False)
+    ddp = bvc.DistributedDataParallel(m, device_ids=None, output_device=None, find_unused_parameters=False,
+                                      bucket_cap_mb=cap)
     res = {"w_after_wrap": m.w.detach().clone().tolist(), "is_module": ddp.module is m,
            "n_params": len(list(ddp.parameters()))}
     # overlapped mode: .grad is None, autograd adopts the views of the stage buffer, which is all-reduced in place
@@ -171,10 +172,16 @@ def _ddp_worker(rank, world, port, out):
     dist.destroy_process_group()
 
 
-def test_bvc_ddp_world2_gloo():
+import pytest  # noqa: E402
+
+
+@pytest.mark.parametrize("cap,port", [(None, 29612), (1.0, 29616)])
+def test_bvc_ddp_world2_gloo(cap, port):
+    """cap None: one collective per stage buffer; cap 1 MB: stage buffers are held back and flushed as one bucket
+    (here at the end of the pass -- the stand-in's 24-byte stage never fills it) -- same gradients either way."""
     mgr = mp.Manager()
     out = mgr.dict()
-    mp.spawn(_ddp_worker, args=(2, 29612, out), nprocs=2, join=True)
+    mp.spawn(_ddp_worker, args=(2, port, out, cap), nprocs=2, join=True)
     x0, x1 = torch.arange(4.0), torch.arange(4.0) + 10
     mean_gw = ((x0 + x1) / 2 * 2.0).tolist()
     for r in (0, 1):

@@ -2,6 +2,8 @@
 (pretrain_videomae.py:187-189) -- on identical parameters and gradients, plain and under GradScaler
 (pretrain_videomae.py:312-314), including a skipped (overflow) step.  fp32 arithmetic with the same operation order:
 the tolerance is a few ulp per step (fma contraction vs separate mul + add), 2e-6."""
+import copy
+
 import pytest
 import torch
 
@@ -143,7 +145,9 @@ def test_fused_adam_matches_torch(cls_name, kw):
     with torch.no_grad():
         for p, q in zip(pa, oc.param_groups[0]["params"]):
             q.copy_(p)
-    oc.load_state_dict(oa.state_dict())
+    # deep copy: Optimizer.load_state_dict keeps tensors that already have the right dtype / device by reference, and
+    # the two optimizers must not share their moment buffers
+    oc.load_state_dict(copy.deepcopy(oa.state_dict()))
     for p, q, g in zip(pa, oc.param_groups[0]["params"], _grads(40, dev)):
         p.grad, q.grad = g.clone(), g.clone()
     oa.step()

@@ -477,15 +477,16 @@ def run_ours(args):
         # DRAM traffic of the dominant kernel: not measurable live (never under a profiler here) -- taken from the
         # committed ncu capture of the same command (profiles/README.md), bytes per launch averaged over one step
         traffic, traffic_src = None, None
-        tpath = os.path.join(ROOT, "profiles", "r01_ncu_step_metrics.json")   # one whole step under ncu, per kernel family
+        tpath = os.path.join(ROOT, "profiles", "r02_ncu_step_metrics.json")   # one whole step under ncu, per kernel family
         tpath_old = os.path.join(ROOT, "profiles", "r01_ncu_gemm_traffic.json")
         if os.path.exists(tpath) and args.config == "base" and B == 64:
             with open(tpath) as f:
                 fam = json.load(f)["families"].get(top["kernel"])
             if fam:
                 traffic = fam["dram_bytes_per_launch"]
-                traffic_src = ("profiles/r01_ncu_step_metrics.json (ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,"
-                               "... --clock-control none -s 3600 -c 1000 python bench.py --steps 2 --warmup 3 --no-cpu; "
+                traffic_src = ("profiles/r02_ncu_step_metrics.json (ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,"
+                               "... --clock-control none -s 3600 -c 900 python bench.py --steps 2 --warmup 3 --no-cpu "
+                               "--no-hf-gpu; "
                                f"average over the {fam['launches']} {top['kernel']} launches of one training step; "
                                f"tensor pipe (UTCHMMA) {fam['tensor_pipe_utchmma_pct_time_weighted']} % of ncu's peak, "
                                "time-weighted)")

@@ -317,3 +317,42 @@ def test_uint8_input_path_is_bit_identical():
     model.set_input_normalization(mean, std)
     lb = model(u8.to(dev), bool_masked_pos=mask).loss
     assert float(la) == float(lb)
+
+
+def test_run_to_run_agreement_and_deterministic_switch():
+    """The one-pass decoder attention backward reduces its dQ contributions with fp32 adds in L2 (TMA reduce) whose
+    order varies from run to run -- as torch's own flash-attention backward does -- and the bf16 roundings downstream
+    amplify those last-bit differences: two backward passes on identical inputs agree to ~2e-5 globally (measured;
+    bound here 2e-4) and ~4e-4 on the deepest tensors (bound 2e-3, still below the bf16 noise against fp32).  Under
+    torch.use_deterministic_algorithms(True) the engine selects the two-pass kernels (no atomics on any activation);
+    what remains is the split-K accumulation of the weight gradients themselves (leaf values, nothing downstream):
+    1e-6 globally, 2e-5 per tensor."""
+    cfg = O.make_config("small")
+    params = O.init_params(cfg, seed=0, perturb=True)
+    x = O.synthetic_clip(2, cfg, seed=3, image_like=True)
+    np.random.seed(3)
+    mask = O.batch_tube_masks(2, cfg.grid, 0.9)
+
+    def worst(ga, gb):
+        rows, g_all = grad_report(ga, gb)
+        tot = sum(v[2] ** 2 for v in rows.values()) ** 0.5
+        return g_all, max(v[0] for v in rows.values() if v[2] >= 1e-3 * tot)
+
+    _, _, g1, _ = run_bvc(cfg, params, x, mask)
+    _, _, g2, _ = run_bvc(cfg, params, x, mask)
+    g_all, g_worst = worst(g1, g2)
+    print(f"[run-to-run/default] global rel-L2 {g_all:.2e}, worst tensor {g_worst:.2e}")
+    assert g_all <= 2e-4 and g_worst <= 2e-3
+    was = torch.are_deterministic_algorithms_enabled()
+    torch.use_deterministic_algorithms(True, warn_only=True)
+    try:
+        _, _, d1, _ = run_bvc(cfg, params, x, mask)
+        _, _, d2, _ = run_bvc(cfg, params, x, mask)
+    finally:
+        torch.use_deterministic_algorithms(was)
+    d_all, d_worst = worst(d1, d2)
+    print(f"[run-to-run/deterministic] global rel-L2 {d_all:.2e}, worst tensor {d_worst:.2e}")
+    assert d_all <= 1e-6 and d_worst <= 2e-5
+    # both kernels compute the same gradient
+    m_all, m_worst = worst(g1, d1)
+    assert m_all <= 2e-4 and m_worst <= 2e-3

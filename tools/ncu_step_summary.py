@@ -16,7 +16,8 @@ from collections import OrderedDict
 
 
 def family(name):
-    for pat, fam in (("gemm_kernel", "gemm"), ("attn_fwd", "attn_fwd"), ("attn_bwd", "attn_bwd"), ("attn_delta", "attn_delta"),
+    for pat, fam in (("gemm_kernel", "gemm"), ("attn(_small)?_fwd", "attn_fwd"), ("attn(_small)?_bwd|attn_dq_convert", "attn_bwd"),
+                     ("attn_delta", "attn_delta"),
                      ("patchify_target", "patchify_target"), ("mask_to_index|mask_count|mask_", "mask"),
                      ("layernorm_fwd", "layernorm_fwd"), ("layernorm_bwd", "layernorm_bwd"), ("colsum", "colsum"),
                      ("sgd", "sgd_step"), ("decoder_mask_rows", "decoder_mask_rows"), ("rows_to_bf16", "rows_to_bf16"),

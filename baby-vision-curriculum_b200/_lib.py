@@ -12,7 +12,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libbvc.so")
-ABI_VERSION = 14
+ABI_VERSION = 15
 
 _lib = None
 
@@ -64,7 +64,7 @@ _SIGNATURES = {
     "bvc_attn_fwd": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_void_p, C.c_void_p,
                                C.c_void_p]),
     "bvc_attn_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
-                               C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+                               C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "bvc_nce_normalize_split": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_float, C.c_void_p,
                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "bvc_nce_partial_slots": (C.c_int64, [C.c_int32]),
@@ -335,12 +335,13 @@ def attn_fwd(qkv, B, S, H, scale, out, lse):
     _count()
 
 
-def attn_bwd(qkv, out, dout, lse, B, S, H, scale, delta, dqkv, dq_accum=None):
-    """dq_accum: optional fp32 [B, S, H, 64] scratch; with it sequences > 160 tokens run the one-pass backward."""
+def attn_bwd(qkv, out, dout, lse, B, S, H, scale, delta, dqkv, dq_accum=None, dq_accum_zeroed=False):
+    """dq_accum: optional fp32 [B, S, H, 64] scratch; with it sequences > 160 tokens run the one-pass backward.
+    dq_accum_zeroed: the caller already cleared it (stream-ordered before this call)."""
     _cuda(qkv, out, dout, lse, delta, dqkv, dq_accum)
     with _Timed("attn_bwd", 8.0 * B * H * S * S * 64, 0.0, f"B{B} S{S} H{H}"):
         _check(load().bvc_attn_bwd(_p(qkv), _p(out), _p(dout), _p(lse), B, S, H, scale, _p(delta), _p(dqkv),
-                                   _p(dq_accum), _stream()), "bvc_attn_bwd")
+                                   _p(dq_accum), int(bool(dq_accum_zeroed)), _stream()), "bvc_attn_bwd")
     _count(3)
 
 

@@ -314,6 +314,23 @@ def _block_bwd(ctx, dxo):
         o += s_
     g_ln1w, g_ln1b, g_wqkv, g_bqkv, g_wo, g_bo, g_ln2w, g_ln2b, g_w1, g_b1, g_w2, g_b2, cs_in = views
 
+    # long sequences (the decoder's 1568 tokens): one-pass attention backward, dQ contributions reduced into an fp32
+    # scratch.  The reduction order of those fp32 adds (TMA reduce, L2 atomics) varies from run to run -- like torch's own
+    # flash attention backward -- so two backward passes agree to ~2e-5 (global rel-L2; up to ~4e-4 on a single deep
+    # tensor, bf16 roundings downstream amplify last-bit differences) instead of bit for bit.  Under
+    # torch.use_deterministic_algorithms(True) (or BVC_ATTN_BWD1=0) the deterministic two-pass kernels run instead.
+    # The scratch is cleared NOW, on the side stream, under the MLP's backward GEMMs (154 MB of writes off the
+    # critical path: 40 us per decoder layer).
+    one_pass = S > 160 and not torch.are_deterministic_algorithms_enabled()
+    dq_acc, dq_zeroed = None, None
+    if one_pass:
+        dq_acc = _empty((B, S, H, 64), F32, dev)
+        if isinstance(wg, _SideStream):
+            with wg.after_main():
+                dq_acc.zero_()
+                dq_zeroed = torch.cuda.Event()
+                dq_zeroed.record()
+
     # fc2: x_out = x_mid + act.W2^T + b2
     d_pre = _empty((M, ff), BF16, dev)
     # x gelu' (saved by the forward epilogue) fused; the epilogue also accumulates the column sums of d_pre = the
@@ -344,14 +361,9 @@ def _block_bwd(ctx, dxo):
     # attention core
     dqkv = _empty((M, 3 * d), BF16, dev)
     delta = _empty((B, H, S), F32, dev)
-    # long sequences (the decoder's 1568 tokens): one-pass backward, dQ contributions reduced into an fp32 scratch.
-    # The reduction order of those fp32 adds (TMA reduce, L2 atomics) varies from run to run -- like torch's own flash
-    # attention backward -- so two backward passes agree to ~2e-5 (global rel-L2; up to ~4e-4 on a single deep tensor,
-    # bf16 roundings downstream amplify last-bit differences) instead of bit for bit.  Under
-    # torch.use_deterministic_algorithms(True) (or BVC_ATTN_BWD1=0) the deterministic two-pass kernels run instead.
-    one_pass = S > 160 and not torch.are_deterministic_algorithms_enabled()
-    dq_acc = _empty((B, S, H, 64), F32, dev) if one_pass else None
-    L.attn_bwd(qkv, attn, d_attn, lse, B, S, H, scale, delta, dqkv, dq_acc)
+    if dq_zeroed is not None:
+        torch.cuda.current_stream().wait_event(dq_zeroed)
+    L.attn_bwd(qkv, attn, d_attn, lse, B, S, H, scale, delta, dqkv, dq_acc, dq_accum_zeroed=dq_zeroed is not None)
     del dq_acc
     # fused QKV projection
     d_u1 = _empty((M, d), BF16, dev)

@@ -28,7 +28,7 @@ extern "C" {
 #define BVC_ERR_ARG (-1)
 #define BVC_ERR_DRIVER (-2)
 #define BVC_ERR_LAUNCH (-3)
-#define BVC_ABI_VERSION 14
+#define BVC_ABI_VERSION 15
 
 /* library / build info: returns BVC_ABI_VERSION (bumped when a signature changes) */
 int bvc_abi_version(void);
@@ -184,12 +184,14 @@ int bvc_decoder_mask_rows(float* x, const float* mask_token, const float* pos, c
  *   dq_accum fp32 [B, S, H, 64] is optional scratch: with it, sequences longer than 160 run the ONE-pass backward
  *   (5 MMAs and one exponential per score; each (key tile, query tile) pair's dQ contribution is added into dq_accum
  *   by TMA reduce and converted into dqkv's q slot afterwards); with NULL the two-pass kernels run (no atomics,
- *   7 MMAs and two exponentials per score).  The call zero-fills dq_accum itself.
+ *   7 MMAs and two exponentials per score).  The call zero-fills dq_accum itself unless dq_accum_zeroed != 0 (the
+ *   caller cleared it earlier, e.g. on another stream while the preceding GEMMs ran).
  * ------------------------------------------------------------------------------------------------------ */
 int bvc_attn_fwd(const void* qkv, int32_t B, int32_t S, int32_t H, float scale, void* out, float* lse,
                  void* stream);
 int bvc_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, int32_t B, int32_t S,
-                 int32_t H, float scale, float* delta, void* dqkv, float* dq_accum, void* stream);
+                 int32_t H, float scale, float* delta, void* dqkv, float* dq_accum, int32_t dq_accum_zeroed,
+                 void* stream);
 
 /* ------------------------------------------------------------------------------------------------------
  * Optimizer step (pretrain_videomae.py:187-197 torch.optim.SGD(nesterov) under GradScaler :312-314) as one

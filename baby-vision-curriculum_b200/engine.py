@@ -304,15 +304,21 @@ def _block_bwd(ctx, dxo):
     dxob, cs_out = st.side.take(dxo, M, d)
     wg = _SideStream(dev) if _WGRAD_STREAM else _NoSideStream()  # operands stay referenced until wg.join() below
 
-    # every atomically-accumulated output of this block in one zero-filled buffer (one memset); the last slot
-    # collects colsum(dx) of this block's input gradient for the stage upstream
-    sizes = [d, d, 3 * d * d, 3 * d, d * d, d, d, d, ff * d, ff, d * ff, d, d]
-    flat = torch.zeros(sum(sizes), dtype=F32, device=dev)
+    # every atomically-accumulated output of this block in one zero-filled buffer (= the all-reduce bucket).  The
+    # vectors (accumulated by main-stream kernels; the last slot collects colsum(dx) of this block's input gradient for the
+    # stage upstream) come first and are cleared here; the four weight matrices -- 99.9 % of the bytes, written only by
+    # the weight-gradient GEMMs on the side stream -- are cleared there, off the critical path.
+    sizes = [d, d, 3 * d, d, d, d, ff, d, d, 3 * d * d, d * d, ff * d, d * ff]
+    n_vec = sum(sizes[:9])
+    flat = torch.empty(sum(sizes), dtype=F32, device=dev)
+    flat[:n_vec].zero_()
+    with wg.after_main():
+        flat[n_vec:].zero_()
     views, o = [], 0
     for s_ in sizes:
         views.append(flat[o:o + s_])
         o += s_
-    g_ln1w, g_ln1b, g_wqkv, g_bqkv, g_wo, g_bo, g_ln2w, g_ln2b, g_w1, g_b1, g_w2, g_b2, cs_in = views
+    g_ln1w, g_ln1b, g_bqkv, g_bo, g_ln2w, g_ln2b, g_b1, g_b2, cs_in, g_wqkv, g_wo, g_w1, g_w2 = views
 
     # long sequences (the decoder's 1568 tokens): one-pass attention backward, dQ contributions reduced into an fp32
     # scratch.  The reduction order of those fp32 adds (TMA reduce, L2 atomics) varies from run to run -- like torch's own

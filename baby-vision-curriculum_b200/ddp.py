@@ -43,8 +43,9 @@ class GradSync:
         # Stage buffers are the buckets; `bucket_bytes` > 0 additionally COALESCES consecutive stages into one NCCL
         # group launch once that many bytes are pending (19 launches per ViT-B step become ~376.8 MB / bucket_bytes):
         # fewer NCCL kernels competing with the persistent GEMMs for SMs.  None: BVC_DDP_BUCKET_MB from the
-        # environment, default 32 (measured, ViT-B step: 2 x B200 26.1 -> 24.1 ms with 96 MB; 8 x B200 24.58 ms with 0,
-        # 24.21 with 32, 24.32 with 96, 24.72 with 400 -- profiles/r02_ddp_bucket_sweep.md); 0: one collective per stage.
+        # environment, default 32 (ViT-B step on 8 x B200: 24.58 ms with 0, 24.21 with 32, 24.32 with 96, 24.72 with 400 --
+        # inside the run-to-run noise of those boxes, profiles/r02_ddp_bucket_sweep.md; 7 launches instead of 19 is kept
+        # for the fewer launches, not for a measured gain); 0: one collective per stage.
         if bucket_bytes is None:
             bucket_bytes = int(float(os.environ.get("BVC_DDP_BUCKET_MB", "32")) * (1 << 20))
         self.bucket_bytes = int(bucket_bytes)

@@ -338,7 +338,28 @@ def run_ours(args):
     # three back-to-back passes of exactly K steps each, ALL reported (value_passes_ms_per_step); `value` is the MEDIAN
     # pass -- no pass is dropped or re-measured on a condition
     n0 = L.launch_count()
+    # host-side evidence for slow passes: Python's cyclic collector, timed through gc.callbacks (BVC_BENCH_GC=off runs the
+    # passes with the collector disabled after a full collection -- what long-running trainers do -- and says so)
+    import gc
+    gc_log, gc_t0 = [], [0.0]
+
+    def gc_cb(phase, info):
+        if phase == "start":
+            gc_t0[0] = time.perf_counter()
+        else:
+            gc_log.append((info.get("generation", -1), 1e3 * (time.perf_counter() - gc_t0[0])))
+    gc_off = os.environ.get("BVC_BENCH_GC", "on") == "off"
+    if gc_off:
+        gc.collect()
+        gc.disable()
+    gc.callbacks.append(gc_cb)
     runs = [timed_pass() for _ in range(3)]
+    gc.callbacks.remove(gc_cb)
+    if gc_off:
+        gc.enable()
+    gc_stats = {"mode": "disabled during the timed passes" if gc_off else "python default",
+                "collections": len(gc_log), "gen2_collections": sum(1 for g_, _ in gc_log if g_ == 2),
+                "total_ms": round(sum(m for _, m in gc_log), 2), "max_ms": round(max([m for _, m in gc_log] or [0.0]), 2)}
     launches = (L.launch_count() - n0) // 3
     t = torch.tensor([r[0] for r in runs], device=dev, dtype=torch.float64)
     if world > 1:
@@ -509,7 +530,7 @@ def run_ours(args):
             "metric": "VideoMAE ViT-B/16 pretrain clips/s" if args.config == "base" else f"VideoMAE ViT-{args.config} clips/s",
             "value": clips * args.steps / (ms / 1e3), "unit": "clips/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "settle_steps": kSettle, "ms_per_step": ms / args.steps,
-            "value_passes_ms_per_step": passes, "step_ms_min_median_max": [min(per_step), statistics.median(per_step),
+            "value_passes_ms_per_step": passes, "python_gc_rank0": gc_stats, "step_ms_min_median_max": [min(per_step), statistics.median(per_step),
                                                                             max(per_step)],
             "step_ms_gpu": [round(v, 2) for v in per_step], "step_ms_host_enqueue": [round(v, 2) for v in timed_pass.host_ms],
             "higher_is_better": True, "scaling": "weak",

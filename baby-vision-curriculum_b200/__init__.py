@@ -15,6 +15,7 @@ from .masking import TubeMaskingGenerator, RandomMaskingGenerator, batch_masks  
 from .ddputils import AllReduce, AllGather  # noqa: F401
 from .optim import FusedSGD, FusedAdam, FusedAdamW  # noqa: F401
 from .ddp import DistributedDataParallel  # noqa: F401
+from .graphed import GraphedTrainStep  # noqa: F401
 from .simclr import info_nce_loss, get_special_matrix, make_masks as make_simclr_masks  # noqa: F401
 from .jepa import (apply_masks, repeat_interleave_batch, jepa_targets, smooth_l1_loss, ema_update,  # noqa: F401
                    MaskCollator, update_masks)

@@ -308,7 +308,11 @@ class VideoMAEForPreTraining(nn.Module):
             return int(cnt[0])
         key = (B, N, str(dev))
         if self.static_mask_count:
-            if self._status_event is not None and self._status_event.query() and int(self._status_host[0]) != 0:
+            # (under CUDA-graph capture no event may be queried: the status copy of a replayed step is checked by the
+            # next eager call, or by check_mask_status())
+            capturing = torch.cuda.is_current_stream_capturing()
+            if not capturing and self._status_event is not None and self._status_event.query() \
+                    and int(self._status_host[0]) != 0:
                 # an earlier call's rows did not match the cached count: forget it and count this mask for real
                 self._status.zero_()
                 self._status_host.zero_()
@@ -438,8 +442,9 @@ class VideoMAEForPreTraining(nn.Module):
             L.mask_to_index(m, nv, st.vis_idx, st.msk_idx, st.slot, st.status)
             if self.static_mask_count:
                 self._status_host.copy_(self._status, non_blocking=True)
-                self._status_event = torch.cuda.Event()
-                self._status_event.record()
+                if not torch.cuda.is_current_stream_capturing():
+                    self._status_event = torch.cuda.Event()
+                    self._status_event.record()
 
             K = C * c.tubelet_size * c.patch_size ** 2
             patches = torch.empty((B * nv, K), dtype=BF16, device=dev)

@@ -40,6 +40,7 @@ class _FusedBase(torch.optim.Optimizer):
         self._pin_events = {}    # group index -> event after the last copy out of the staging buffer
         self.table_builds = 0    # how often a pointer table had to be rebuilt (stable pointers -> stays small)
         self._found_inf = {}     # device -> fp32 scalar written by bvc_grad_nonfinite
+        self._graph_pins = []    # pinned pointer tables referenced by captured CUDA graphs
 
     def _shadow_model(self):
         m = self._shadow_from
@@ -84,12 +85,19 @@ class _FusedBase(torch.optim.Optimizer):
         # gradient buffers new addresses now and then, and a pageable copy here was a hidden synchronisation
         n, n_extra = len(rows), (len(self._state_keys) - 1 if has_state else 0)
         words = 6 * n + n_extra * n
-        ev = self._pin_events.get(gi)
-        if ev is not None:
-            ev.synchronize()  # the previous copy out of the staging buffer (long done)
-        pin = self._pinned.get(gi)
-        if pin is None or pin.numel() < words:
-            pin = self._pinned[gi] = torch.empty(max(words, 64), dtype=torch.int64).pin_memory()
+        capturing = torch.cuda.is_current_stream_capturing()
+        if capturing:
+            # CUDA-graph capture: the copy below becomes a node that re-reads its pinned source at every replay, and no
+            # event may be queried or synchronised -- a staging buffer of its own, kept alive with the optimizer
+            pin = torch.empty(max(words, 64), dtype=torch.int64).pin_memory()
+            self._graph_pins.append(pin)
+        else:
+            ev = self._pin_events.get(gi)
+            if ev is not None:
+                ev.synchronize()  # the previous copy out of the staging buffer (long done)
+            pin = self._pinned.get(gi)
+            if pin is None or pin.numel() < words:
+                pin = self._pinned[gi] = torch.empty(max(words, 64), dtype=torch.int64).pin_memory()
         host = pin.numpy()
         host[:6 * n] = np.array(rows, dtype=np.int64).reshape(-1)
         for j in range(n_extra):
@@ -97,9 +105,10 @@ class _FusedBase(torch.optim.Optimizer):
         dev = plist[0].device
         dev_tab = torch.empty(words, dtype=torch.int64, device=dev)
         dev_tab.copy_(pin[:words], non_blocking=True)
-        ev = torch.cuda.Event()
-        ev.record(torch.cuda.current_stream(dev))
-        self._pin_events[gi] = ev
+        if not capturing:
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(dev))
+            self._pin_events[gi] = ev
         total = int(sum(r[4] for r in rows))
         n_shadow = int(sum(r[4] for r in rows if r[3]))
         cached = (key, dev_tab, n, total, n_shadow)

@@ -19,7 +19,7 @@ def test_bvc_ddp_parity_two_gpus():
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
            "127.0.0.1", "--master-port", "29655", os.path.join(ROOT, "tools", "ddp_parity.py"), "--config", "base",
            "--batch", "8"]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=420, cwd=ROOT)
     lines = [ln for ln in r.stdout.splitlines() if ln.startswith(("PASS", "FAIL", "DDP-PARITY"))]
     fails = [ln for ln in lines if ln.startswith("FAIL")]
     assert r.returncode == 0 and not fails and any("ALL PASS" in ln for ln in lines), \

@@ -287,7 +287,7 @@ def run_ours(args):
         scaler.scale(loss).backward()
         scaler.step(opt)
         scaler.update()
-        return loss
+        return loss.detach()  # (a loss kept with its autograd graph would pin the AccumulateGrad nodes: graphed.py)
 
     def barrier():
         if world > 1:
@@ -462,6 +462,59 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_e2e, ms_e2e_u8 = float(t[0]), float(t[1])
 
+    # ------------------------------------------------------------------ the same loop body replayed from ONE CUDA graph
+    # (bvc_b200.GraphedTrainStep): at this batch the GPU is the bound either way; at the batch the reference's own SLURM
+    # scripts use (16 clips per GPU) the eager loop is launch-bound (~360 launches from Python per step) and the
+    # replayed one is not.  Reported next to `value`, which stays the eager, reference-verbatim loop.
+    graph_info = None
+    if args.optimizer == "fused" and (world == 1 or args.ddp == "bvc") and not args.no_graph:
+        import gc as _gc
+
+        def time_steps(fn, n):
+            barrier()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            h0 = time.perf_counter()
+            a0.record()
+            for i in range(n):
+                fn(i)
+            a1.record()
+            h1 = time.perf_counter()
+            barrier()
+            tt = torch.tensor([a0.elapsed_time(a1)], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            return float(tt[0]) / n, 1e3 * (h1 - h0) / n
+
+        try:
+            gstep = bvc.GraphedTrainStep(xmodel, opt, scaler, loss_fn=bvc.AllReduce.apply, warmup=2)
+            for i in range(4):  # 2 eager warm-up calls, the capture, one more replay
+                gstep(dev_clips[i % n_pool], dev_masks[i % 8])
+            g_ms, g_host = time_steps(lambda i: gstep(dev_clips[i % n_pool], dev_masks[i % 8]), args.steps)
+            graph_info = {"api": "bvc_b200.GraphedTrainStep (pretrain_videomae.py:292-314 captured once, replayed)",
+                          "value": B * world / (g_ms / 1e3), "unit": "clips/s", "ms_per_step": g_ms,
+                          "host_ms_per_step": g_host, "captures": gstep.captures}
+            del gstep
+            if world == 1:
+                sb = 16
+                sc16 = [t[:sb].contiguous() for t in dev_clips]
+                sm16 = [t[:sb].contiguous() for t in dev_masks]
+                for i in range(3):
+                    train_step(sc16[i % n_pool], sm16[i % 8])
+                e_ms, e_host = time_steps(lambda i: train_step(sc16[i % n_pool], sm16[i % 8]), 2 * args.steps)
+                g16 = bvc.GraphedTrainStep(xmodel, opt, scaler, loss_fn=bvc.AllReduce.apply, warmup=2)
+                for i in range(4):
+                    g16(sc16[i % n_pool], sm16[i % 8])
+                s_ms, s_host = time_steps(lambda i: g16(sc16[i % n_pool], sm16[i % 8]), 2 * args.steps)
+                graph_info["small_batch"] = {
+                    "batch_per_gpu": sb, "why": "the reference's SLURM scripts train at 16 clips per GPU",
+                    "eager_clips_per_s": sb / (e_ms / 1e3), "eager_ms_per_step": e_ms, "eager_host_ms_per_step": e_host,
+                    "graphed_clips_per_s": sb / (s_ms / 1e3), "graphed_ms_per_step": s_ms, "graphed_host_ms_per_step": s_host}
+                del g16
+        except Exception as e:  # reported, never fatal for the primary numbers above
+            graph_info = {"error": f"{type(e).__name__}: {str(e)[:300]}"}
+        _gc.collect()   # captured graphs hold NCCL work: released before the process group goes
+        torch.cuda.synchronize()
+
     # ------------------------------------------------------------------ secondary bar: the LIBRARY path on the same GPU
     # (BASELINE.md section 5): the unmodified HF VideoMAEForPreTraining under torch.autocast(bf16) -- cuDNN conv3d,
     # cuBLASLt, SDPA -- running the same step at the same batch in this very process, after our measurements
@@ -553,7 +606,7 @@ def run_ours(args):
                                 "note": "same loop, uint8 frames; ToTensor + Normalize(0.5, 0.25) inside the patchify "
                                         "kernel (bit-identical to host normalisation)"},
             "gpu_launches": launches, "roofline": roof, "kernels": kernels, "cpu_baseline": cpu, "clocks": clocks,
-            "loss_last": last_loss, "gpu_library_baseline": gpu_lib, "ddp_check": ddp_check,
+            "loss_last": last_loss, "gpu_library_baseline": gpu_lib, "ddp_check": ddp_check, "cuda_graph": graph_info,
         }
         print(json.dumps(out))
         if args.detail:
@@ -563,7 +616,8 @@ def run_ours(args):
             with open(args.detail, "w") as f:
                 json.dump(rows, f, indent=1)
     if world > 1:
-        dist.destroy_process_group()
+        dist.barrier()   # every rank is past its last collective; the process group is torn down by __main__, after the
+        torch.cuda.synchronize()   # JSON line is out
 
 
 def run_reference(args):
@@ -596,6 +650,7 @@ if __name__ == "__main__":
     ap.add_argument("--cpu-steps", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-hf-gpu", action="store_true", help="skip the HF bf16-autocast run on the same GPU")
+    ap.add_argument("--no-graph", action="store_true", help="skip the CUDA-graph replay of the step (cuda_graph key)")
     ap.add_argument("--ddp", default="bvc", choices=["bvc", "torch"],
                     help="N > 1: bvc.DistributedDataParallel (per-stage in-place all-reduce) or torch's DDP")
     ap.add_argument("--optimizer", default="fused", choices=["fused", "torch"],
@@ -618,3 +673,11 @@ if __name__ == "__main__":
         sys.stderr.write(ln + "\n")
     if _lines:
         os.write(_json_fd, (_lines[-1] + "\n").encode())
+    import torch.distributed as _dist
+    if _dist.is_available() and _dist.is_initialized():
+        # communicator teardown after CUDA-graph captures of NCCL work has been seen to hang (tools/ddp_parity.py): the
+        # result is written -- leave without the teardown if it does not return promptly
+        sys.stderr.flush()
+        threading.Timer(20.0, lambda: os._exit(0)).start()
+        _dist.destroy_process_group()
+        os._exit(0)

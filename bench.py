@@ -593,7 +593,8 @@ def run_ours(args):
                                "launch and the weight-gradient side stream off (ms_per_step_profiled); `value` comes "
                                "from the first pass, without the events and with the side stream"}
         step_flops = flops_per_clip(c) * B
-        cpu = cpu_reference(args.config, args.cpu_batch, args.cpu_steps, 1) if not args.no_cpu else None
+        # rank 0 at N = 1 only (under torchrun the other ranks' host threads spin on their streams next to it)
+        cpu = cpu_reference(args.config, args.cpu_batch, args.cpu_steps, 1) if (not args.no_cpu and world == 1) else None
         clips = B * world
         out = {
             "metric": "VideoMAE ViT-B/16 pretrain clips/s" if args.config == "base" else f"VideoMAE ViT-{args.config} clips/s",

@@ -76,7 +76,9 @@ class GraphedTrainStep:
         else:
             loss.backward()
             self.optimizer.step()
-        return loss
+        # detached: the step is complete, and a loss kept alive with its autograd graph would pin this iteration's
+        # AccumulateGrad nodes (and their stream) into the next one
+        return loss.detach()
 
     def _on_side_stream(self, fn, dev):
         if self._stream is None:
@@ -93,8 +95,6 @@ class GraphedTrainStep:
         return (tuple(x.shape), x.dtype, tuple(m.shape), m.dtype, str(x.device), hp)
 
     def _capture(self, x, m):
-        if not (x.is_cuda and m.is_cuda):
-            raise L.BvcError("GraphedTrainStep: inputs and masks must be CUDA tensors (copy them with non_blocking=True)")
         self._x = torch.empty_like(x)
         self._m = torch.empty_like(m)
         self._x.copy_(x)
@@ -117,6 +117,9 @@ class GraphedTrainStep:
         self.captures += 1
 
     def __call__(self, pixel_values, bool_masked_pos):
+        if not (pixel_values.is_cuda and bool_masked_pos.is_cuda):
+            raise L.BvcError("GraphedTrainStep: inputs and masks must be CUDA tensors (there is no CPU path; copy them "
+                             "with .to(device, non_blocking=True) as the reference loop does)")
         self.calls += 1
         if self.calls <= self.warmup:
             return self._on_side_stream(lambda: self._eager(pixel_values, bool_masked_pos), pixel_values.device)

@@ -169,3 +169,24 @@ def test_jepa_host_mirror_validates_before_touching_cuda():
         bvc.jepa_targets(torch.randn(2, 10, 6), [torch.zeros(2, 3, dtype=torch.int64)], 1)   # D % 4 != 0
     with pytest.raises(bvc.BvcError):
         bvc.apply_masks(x, [torch.zeros(2, 3, dtype=torch.int64)])
+
+
+def test_graphed_train_step_host_side(bvc):
+    """GraphedTrainStep validates its arguments without touching CUDA, switches the model to the device-validated
+    visible-token count, and (like every other entry point) has no CPU path."""
+    from tests.helpers import bvc_config
+    cfg = O.make_config("tiny")
+    m = bvc.VideoMAEForPreTraining(bvc_config(cfg))
+    opt = torch.optim.SGD(m.parameters(), lr=0.1)
+    assert m.static_mask_count is False
+    step = bvc.GraphedTrainStep(m, opt, None, warmup=2)
+    assert m.static_mask_count is True and (step.calls, step.captures, step.replays) == (0, 0, 0)
+    with pytest.raises(ValueError):
+        bvc.GraphedTrainStep(m, opt, None, warmup=1)
+    with pytest.raises(TypeError):
+        bvc.GraphedTrainStep(torch.nn.Linear(2, 2), opt, None)
+    x = O.synthetic_clip(1, cfg, seed=0)
+    np.random.seed(0)
+    mask = O.batch_tube_masks(1, cfg.grid, 0.5)
+    with pytest.raises(bvc.BvcError):  # CPU tensors: the eager warm-up call reaches the model, which has no CPU path
+        step(x, mask)

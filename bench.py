@@ -259,6 +259,10 @@ def run_ours(args):
         sampler.start()
     torch.manual_seed(0)
     model = bvc.VideoMAEForPreTraining(bvc.VideoMAEConfig(**c)).to(dev).train()
+    # BVC_BENCH_STATIC_MASK=1: read the visible-token count back once and validate it on the device every step instead
+    # of the model's default (one small synchronising read-back per step).  Measured: no difference in `value`
+    # (2738 vs 2730 clips/s) -- the step is GPU-bound either way -- so the bench keeps the model's default.
+    model.static_mask_count = os.environ.get("BVC_BENCH_STATIC_MASK", "0") == "1"
     xmodel = model
     if world > 1:
         # the reference's line is DDP(xmodel, device_ids=[rank], output_device=rank, find_unused_parameters=False)
@@ -609,7 +613,10 @@ def run_ours(args):
                                    f"GradScaler/{'bvc.FusedSGD' if args.optimizer == 'fused' else 'torch.optim.SGD'}-nesterov), 16x224x224 clips, "
                                    f"tube mask 0.9, batch {B}/GPU",
                        "global_batch": clips, "parallelism": f"dp{world}" + (f" ({args.ddp} DDP)" if world > 1 else ""),
-                       "numa_cpus_bound_rank0": numa, "l2": "inputs larger than L2 "
+                       "numa_cpus_bound_rank0": numa,
+                       "mask_count": ("read back once, validated on the device every step (model.static_mask_count)"
+                                      if model.static_mask_count else "read back every step"),
+                       "l2": "inputs larger than L2 "
                        "(616 MB clip batch per step, alternating between two resident batches)"},
             "ms_per_step_profiled": ms_prof / args.steps,
             "model_tflops_per_gpu": step_flops / (ms / args.steps) / 1e9,

@@ -61,6 +61,7 @@ class GradSync:
         backend = dist.get_backend(process_group)
         self._avg = backend == "nccl"   # gloo (CPU tests) has no AVG: SUM then scale
         self.launched = 0               # collectives launched (bench / tests)
+        self.flushes = 0                # coalesced buckets flushed (one NCCL group launch each)
         self.adopted = 0                # .grad tensors found aliasing their reduced stage buffer (last pass)
         self.copied = 0                 # .grad tensors that had to be overwritten with the reduced view (last pass)
 
@@ -100,6 +101,7 @@ class GradSync:
         pend, self._pending, self._pending_bytes = self._pending, [], 0
         if not pend:
             return
+        self.flushes += 1
         if len(pend) == 1 or not self._avg:
             for t in pend:
                 self._launch(t)

@@ -34,6 +34,34 @@ def test_library_exports_every_declared_symbol(bvc):
     assert lib.bvc_smooth_l1_slots(1) == 1 and lib.bvc_smooth_l1_slots(10 ** 9) > 1
 
 
+def test_plain_c_host_compiles_and_links_against_the_header(bvc, tmp_path):
+    """"a C/C++ host links the same way".  include/bvc.h must be valid C (not only C++), and a host
+    program that references EVERY declared entry point must link against libbvc.so and run without a GPU (nothing is
+    launched: only bvc_abi_version and the host-only bookkeeping calls are executed)."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    hdr = open(os.path.join(ROOT, "include", "bvc.h")).read()
+    declared = sorted(set(re.findall(r"\b(bvc_[a-z0-9_]+)\s*\(", hdr)))
+    table = ",\n".join(f"  (void (*)(void)){n}" for n in declared)
+    src = tmp_path / "host.c"
+    src.write_text(
+        '#include <stdio.h>\n#include "bvc.h"\n'
+        f"static void (*const entry[])(void) = {{\n{table}\n}};\n"
+        "int main(void) {\n"
+        "  unsigned n = 0, i;\n"
+        "  for (i = 0; i < sizeof entry / sizeof entry[0]; ++i) n += entry[i] != 0;\n"
+        '  printf("%d %u %ld\\n", bvc_abi_version(), n, (long)bvc_gemm_loss_slots(256, 512, 256));\n'
+        "  return bvc_abi_version() == BVC_ABI_VERSION ? 0 : 1;\n}\n")
+    libdir = os.path.dirname(bvc._lib.LIB_PATH)
+    exe = tmp_path / "host"
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+                           str(src), "-o", str(exe), "-L", libdir, "-lbvc", f"-Wl,-rpath,{libdir}"])
+    out = subprocess.check_output([str(exe)], text=True).split()
+    assert out == [str(bvc._lib.ABI_VERSION), str(len(declared)), "32"]
+
+
 def test_masking_mirror_matches_reference_fixtures(bvc, golden_dir):
     g = np.load(os.path.join(golden_dir, "masks.npz"))
     np.random.seed(0)

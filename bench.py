@@ -672,7 +672,8 @@ if __name__ == "__main__":
     ap.add_argument("--config", default="base", choices=sorted(CONFIGS))
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--cpu-batch", type=int, default=4)
-    ap.add_argument("--cpu-steps", type=int, default=3)
+    ap.add_argument("--cpu-steps", type=int, default=20,
+                    help="timed steps of the cpu_baseline sample (batch --cpu-batch): ~12 s of CPU work on 16 cores")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-hf-gpu", action="store_true", help="skip the HF bf16-autocast run on the same GPU")
     ap.add_argument("--no-graph", action="store_true", help="skip the CUDA-graph replay of the step (cuda_graph key)")

@@ -262,3 +262,32 @@ def test_gelu_fit_in_the_gemm_epilogue_is_exact_erf_gelu_to_fp32_noise():
     grad = x64 * pdf + cdf
     exact = special.ndtr(x64) + x64 * np.exp(-0.5 * x64 * x64) / np.sqrt(2 * np.pi)
     assert np.abs(grad - exact).max() <= 4e-6
+
+
+def test_every_entry_point_rejects_null_arguments_before_touching_cuda(bvc):
+    """Error behaviour of the C ABI (include/bvc.h: "returns 0 on success, <0 on error; never throws"): every entry
+    point called with null pointers and zero sizes returns BVC_ERR_ARG from its host-side validation -- no crash, no
+    CUDA call (this runs without a GPU), one diagnostic line on stderr.  In a child process, so that a crash would be a
+    test failure and not the end of the test session."""
+    import subprocess
+    import sys
+    code = r'''
+import ctypes as C, sys
+sys.path.insert(0, %r)
+from bvc_b200 import _lib as L
+lib = L.load()
+n = 0
+for name, (res, args) in L._SIGNATURES.items():
+    if res is not C.c_int or not args:
+        continue
+    vals = [0 if a in (C.c_int32, C.c_int64, C.c_int) else 0.0 if a in (C.c_float, C.c_double) else None for a in args]
+    rc = getattr(lib, name)(*vals)
+    assert rc == -1, (name, rc)
+    n += 1
+print("REJECTED", n)
+''' % ROOT
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    n_int = sum(1 for res, args in bvc._lib._SIGNATURES.values() if res is __import__("ctypes").c_int and args)
+    assert r.stdout.split() == ["REJECTED", str(n_int)] and n_int >= 29
+    assert r.stderr.count("bvc: bad argument") == n_int

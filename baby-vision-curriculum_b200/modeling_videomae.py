@@ -197,6 +197,11 @@ class VideoMAEForPreTraining(nn.Module):
             raise NotImplementedError("the sm_100a attention kernels are built for head_dim 64")
         if c.num_channels != 3 or c.patch_size != 16 or c.tubelet_size not in (1, 2):
             raise NotImplementedError("patchify kernel: 3 channels, 16x16 patches, tubelet 1 or 2")
+        if max(c.hidden_size, c.decoder_hidden_size) > 1024 or c.image_size > 256 or c.image_size % c.patch_size or \
+                c.num_frames % c.tubelet_size:
+            raise NotImplementedError("LayerNorm kernels keep a row in registers (width <= 1024: up to ViT-L); the "
+                                      "patchify kernel takes frames of whole 16x16 patches up to 256 pixels wide and "
+                                      "whole tubelets")
         self.config = c
         self.output_logits = output_logits
         self.videomae = VideoMAEModel(c)

@@ -127,6 +127,11 @@ def test_unsupported_configs_fail_loudly(bvc):
         bvc.VideoMAEForPreTraining(bvc.VideoMAEConfig(num_attention_heads=8))  # head_dim 96
     with pytest.raises(NotImplementedError):
         bvc.VideoMAEForPreTraining(bvc.VideoMAEConfig(use_mean_pooling=False))
+    # limits of the kernels (include/bvc.h) surface at construction, not as a failed launch in the first forward
+    for kw in (dict(hidden_size=1280, num_attention_heads=20, intermediate_size=5120), dict(image_size=384),
+               dict(image_size=200), dict(num_frames=15), dict(patch_size=14), dict(tubelet_size=4)):
+        with pytest.raises(NotImplementedError):
+            bvc.VideoMAEForPreTraining(bvc.VideoMAEConfig(**kw))
 
 
 def test_bench_flop_model_matches_baseline_md():
@@ -291,3 +296,59 @@ print("REJECTED", n)
     n_int = sum(1 for res, args in bvc._lib._SIGNATURES.values() if res is __import__("ctypes").c_int and args)
     assert r.stdout.split() == ["REJECTED", str(n_int)] and n_int >= 29
     assert r.stderr.count("bvc: bad argument") == n_int
+
+
+def test_gemm_entry_point_argument_contract(bvc):
+    """bvc_gemm_bf16's documented preconditions (include/bvc.h), each violated alone with otherwise valid arguments and
+    fake, never dereferenced device addresses: BVC_ERR_ARG before any CUDA call."""
+    import ctypes as C
+    lib = bvc._lib.load()
+    P = 0x10000  # 16-byte aligned fake device address
+
+    def call(**over):
+        kw = dict(a=P, b=P + 0x1000, lda=64, ldb=64, a_mn_major=0, b_mn_major=0, M=128, N=64, K=64, k_splits=1,
+                  out_f32=None, out_bf16=P + 0x2000, ldo=64, alpha_host=1.0, act=0, ld_aux=0, ldr=0, ldt=0,
+                  block_n=0, cta_pair=0)
+        kw.update(over)
+        args = bvc._lib.GemmArgs(**kw)
+        return lib.bvc_gemm_bf16(C.byref(args), None)
+
+    bad = [dict(a=None), dict(b=None), dict(M=0), dict(K=-1), dict(N=60), dict(lda=60), dict(ldb=68), dict(ldo=4),
+           dict(block_n=100), dict(cta_pair=3), dict(out_bf16=None), dict(a=P + 8), dict(b=P + 0x1004),
+           dict(act=3), dict(act=2), dict(act=1, ld_aux=12), dict(res=P, ldr=6),
+           dict(target=P, ldt=64, loss_partial=None), dict(target=P, ldt=6, loss_partial=P),
+           dict(colsum=P, k_splits=2), dict(colsum=P, out_seg=16), dict(colsum=P, target=P, ldt=64, loss_partial=P),
+           dict(lda=32), dict(ldb=32), dict(a_mn_major=1, lda=64, M=128), dict(b_mn_major=1, ldb=32, N=64),
+           dict(cta_pair=2, block_n=192, b_mn_major=1, ldb=256, N=256), dict(cta_pair=2, block_n=64)]
+    for over in bad:
+        assert call(**over) == -1, over
+
+
+def test_patchify_layernorm_attention_argument_contracts(bvc):
+    """The same for the other entry points with documented limits (include/bvc.h): 3 channels, 16 x 16 patches, tubelet
+    1 or 2, W <= 256 and whole patches for the patchify pass; d % 4 == 0, d <= the register-resident row limit and
+    ld >= d for LayerNorm; 16-byte aligned operands for attention; a zero std for the uint8 path."""
+    import ctypes as C
+    lib = bvc._lib.load()
+    P = 0x10000
+
+    def patchify(pixels=P, B=2, T=16, Cc=3, H=224, W=224, ts=2, ps=16, nv=160):
+        return lib.bvc_patchify_target(pixels, P, B, T, Cc, H, W, ts, ps, nv, P, P, 1, None)
+
+    for kw in (dict(Cc=4), dict(ps=8), dict(ts=3), dict(ts=4), dict(T=15), dict(H=220), dict(W=232), dict(W=272),
+               dict(B=0), dict(pixels=P + 4), dict(nv=1569), dict(nv=-1), dict(pixels=None)):
+        assert patchify(**kw) == -1, kw
+    f3 = C.c_float * 3
+    u8 = lambda mean, std: lib.bvc_patchify_target_u8(P, mean, std, P, 2, 16, 3, 224, 224, 2, 16, 160, P, P, 1, None)  # noqa: E731
+    assert u8(f3(0.5, 0.5, 0.5), f3(0.25, 0.0, 0.25)) == -1      # std 0: the division of homeview.py:222 is undefined
+    assert u8(None, f3(0.25, 0.25, 0.25)) == -1 and u8(f3(0.5, 0.5, 0.5), None) == -1
+
+    def ln(d=768, ldx=768, M=64):
+        return lib.bvc_layernorm_fwd(P, ldx, 0, 0, 0, P, P, 1e-12, M, d, P, P, P, None)
+
+    for kw in (dict(d=770), dict(d=0), dict(M=0), dict(ldx=512), dict(ldx=770), dict(d=1 << 20, ldx=1 << 20)):
+        assert ln(**kw) == -1, kw
+    assert lib.bvc_attn_fwd(P + 8, 2, 160, 12, 0.125, P, P, None) == -1
+    assert lib.bvc_attn_fwd(P, 2, 0, 12, 0.125, P, P, None) == -1
+    assert lib.bvc_attn_bwd(P, P, P + 2, P, 2, 160, 12, 0.125, P, P, None, 0, None) == -1
+    assert lib.bvc_mask_to_index(P, 2, 1568, 1569, P, P, P, P, None) == -1
